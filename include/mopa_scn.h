@@ -1,0 +1,161 @@
+/* mopa_scn.h -- C ABI of libmopa_scn.so, the B200 (sm_100a) replacement for the native layer behind
+ * `import sparseconvnet as scn` on MoPA's 3D-branch hot path.
+ *
+ * The reference reaches native code only through the SparseConvNet Python modules assembled at
+ *   /root/reference/mopa/models/scn_unet.py:25-30   (InputLayer, SubmanifoldConvolution, UNet, BatchNormReLU, OutputLayer)
+ * and, through scn.UNet, Convolution / Deconvolution / BatchNormLeakyReLU / ConcatTable / JoinTable.
+ * Upstream binds those modules to a pybind11 module `sparseconvnet.SCN` ([UPSTREAM] sparseconvnet/SCN/pybind.cpp,
+ * sparseconvnet.h; not vendored under /root/reference). Every entry point below names
+ * the upstream binding it replaces; argument meaning follows that binding, with these deliberate differences:
+ *   - plain C: raw pointers + sizes + an explicit CUDA stream, no torch types, status code + last_error();
+ *   - the callee never allocates feature tensors: a *_prepare / setLocations call returns the row count, the
+ *     caller (PyTorch) allocates, then *_updateOutput fills;
+ *   - coordinates are hashed ON THE GPU (upstream builds grids and rulebooks on the host even for CUDA tensors);
+ *   - feature matrices carry an explicit row stride (ld, in floats) so JoinTable can be a view of one buffer.
+ *
+ * All feature / weight / gradient pointers are DEVICE pointers to float32 unless a parameter says HOST.
+ * All functions return 0 on success, non-zero on error (message via mopa_scn_last_error(), thread-local).
+ * The library is re-entrant per metadata handle and keeps no global mutable state besides the per-thread error string.
+ */
+#ifndef MOPA_SCN_H_
+#define MOPA_SCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOPA_SCN_ABI_VERSION 1
+
+/* arithmetic mode of the conv contractions (fp32 storage and fp32 accumulation in both) */
+#define MOPA_SCN_PREC_FP32 0 /* 3xTF32 split-operand MMA: fp32-equivalent products (parity mode) */
+#define MOPA_SCN_PREC_TF32 1 /* single TF32 MMA, operands rounded to nearest tf32 (default, fast) */
+
+typedef struct mopa_scn_metadata mopa_scn_metadata; /* replaces [UPSTREAM] Metadata<3> (Metadata/Metadata.h) */
+
+int mopa_scn_abi_version(void);
+const char *mopa_scn_last_error(void);
+
+/* ---- Metadata<3>: owns the per-level GPU hash grids, neighbour tables and rulebooks of ONE forward ------------- */
+mopa_scn_metadata *mopa_scn_Metadata_new(int dimension /* must be 3 */, int device);
+void mopa_scn_Metadata_delete(mopa_scn_metadata *m);
+
+/* replaces InputLayer_updateOutput's rule-building half ([UPSTREAM] IOLayersRules.h::inputLayerRules, mode 4).
+ * coords: int64 (n, ncols), ncols 3 or 4 (x, y, z[, batch]) -- collate.py:182-186 layout. coords_on_device = 0 means a
+ * HOST pointer (what the reference passes; copied H2D on `stream`). Voxel ids = order of first occurrence.
+ * Fails (non-zero) on coordinates outside [0, spatial_size) -- the reference filters them (nuscenes_dataloader.py:422).
+ * Synchronises `stream` once to return the active-site count. */
+int mopa_scn_InputLayer_setLocations(mopa_scn_metadata *m, int64_t spatial_size, const int64_t *coords, int64_t n,
+                                     int ncols, int coords_on_device, int mode /* 4 */, void *stream,
+                                     int64_t *n_active_out);
+/* replaces InputLayer_updateOutput (feature half): out[v] = sum_{i in v, ascending} (1/n_v) * in[i]; in (n, planes) */
+int mopa_scn_InputLayer_updateOutput(mopa_scn_metadata *m, const float *in, int64_t ld_in, int planes, float *out,
+                                     int64_t ld_out, void *stream);
+/* replaces InputLayer_updateGradInput: d_in[i] = (1/n_v) * d_out[voxel(i)] */
+int mopa_scn_InputLayer_updateGradInput(mopa_scn_metadata *m, float *d_in, int64_t ld_din, const float *d_out,
+                                        int64_t ld_dout, int planes, void *stream);
+/* replaces OutputLayer_updateOutput: out[i] = in[voxel(i)]  (n rows out) */
+int mopa_scn_OutputLayer_updateOutput(mopa_scn_metadata *m, const float *in, int64_t ld_in, int planes, float *out,
+                                      int64_t ld_out, void *stream);
+/* replaces OutputLayer_updateGradInput: d_in[v] = sum_{i in v, ascending} d_out[i] */
+int mopa_scn_OutputLayer_updateGradInput(mopa_scn_metadata *m, float *d_in, int64_t ld_din, const float *d_out,
+                                         int64_t ld_dout, int planes, void *stream);
+
+/* replaces Metadata::getSubmanifoldRuleBook (built lazily, cached per spatial size). filter_size must be 3. */
+int mopa_scn_Metadata_prepareSubmanifold(mopa_scn_metadata *m, int64_t spatial_size, int filter_size, void *stream,
+                                         int64_t *n_active_out);
+/* replaces Metadata::getRuleBook(in, out, size, stride) for size == stride == 2: creates the out_size grid if absent. */
+int mopa_scn_Metadata_prepareConvolution(mopa_scn_metadata *m, int64_t in_spatial_size, int64_t out_spatial_size,
+                                         int filter_size, int filter_stride, void *stream, int64_t *n_active_out);
+/* number of active sites at a spatial size already built, or -1 */
+int64_t mopa_scn_Metadata_getNActive(mopa_scn_metadata *m, int64_t spatial_size);
+int64_t mopa_scn_Metadata_getNPoints(mopa_scn_metadata *m);
+
+/* ---- inspection (parity tests): copy integer structures to HOST buffers; each synchronises ------------------- */
+/* voxel coordinates (n_active, 4) int64 [x, y, z, batch] in id order */
+int mopa_scn_Metadata_getSpatialLocations(mopa_scn_metadata *m, int64_t spatial_size, int64_t *coords_host);
+/* point -> voxel id (n_points) */
+int mopa_scn_Metadata_getPointToVoxel(mopa_scn_metadata *m, int32_t *p2v_host);
+/* per-voxel contributing rows, CSR: off (n_active + 1), rows (n_points) ascending within a voxel */
+int mopa_scn_Metadata_getInputRules(mopa_scn_metadata *m, int32_t *off_host, int32_t *rows_host);
+/* submanifold rulebook: counts_host[27]; pairs_host (sum counts, 2) int32 [in, out], offset-major, ascending out.
+ * pairs_host may be NULL to query counts only. */
+int mopa_scn_Metadata_getSubmanifoldRuleBook(mopa_scn_metadata *m, int64_t spatial_size, int64_t *counts_host,
+                                             int32_t *pairs_host);
+/* strided rulebook in_size -> in_size/2: counts_host[8]; pairs (n_active(in), 2) [fine, coarse], offset-major */
+int mopa_scn_Metadata_getConvolutionRuleBook(mopa_scn_metadata *m, int64_t in_spatial_size, int64_t *counts_host,
+                                             int32_t *pairs_host);
+
+/* ---- weights: repack (volume, nIn, nOut) fp32 into the MMA fragment order the conv kernels stream -------------
+ * transpose = 0: forward operand. transpose = 1: operand of the input-gradient pass (W[k]^T; for submanifold
+ * filters additionally offset-flipped, k -> volume-1-k). Output size from _packedWeightFloats. */
+int64_t mopa_scn_packedWeightFloats(int volume, int n_in, int n_out, int precision);
+int mopa_scn_packWeights(const float *weight, int volume, int n_in, int n_out, int transpose, int flip, int precision,
+                         float *packed, void *stream);
+
+/* ---- convolutions ---------------------------------------------------------------------------------------------
+ * *_updateOutput replace SubmanifoldConvolution_updateOutput / Convolution_updateOutput / Deconvolution_updateOutput
+ * ([UPSTREAM] CUDA/Convolution.cu, Deconvolution.cu); bias is not supported (scn_unet.py passes bias=False everywhere).
+ * `packed` = mopa_scn_packWeights(weight, transpose=0). Output rows are written once (no atomics, k ascending). */
+int mopa_scn_SubmanifoldConvolution_updateOutput(mopa_scn_metadata *m, int64_t spatial_size, int filter_size,
+                                                 const float *in, int64_t ld_in, float *out, int64_t ld_out,
+                                                 const float *weight, const float *packed, int n_in, int n_out,
+                                                 int precision, void *stream);
+int mopa_scn_Convolution_updateOutput(mopa_scn_metadata *m, int64_t in_spatial_size, int64_t out_spatial_size,
+                                      int filter_size, int filter_stride, const float *in, int64_t ld_in, float *out,
+                                      int64_t ld_out, const float *weight, const float *packed, int n_in, int n_out,
+                                      int precision, void *stream);
+/* in_spatial_size is the COARSE size, out_spatial_size the fine one (existing grid) */
+int mopa_scn_Deconvolution_updateOutput(mopa_scn_metadata *m, int64_t in_spatial_size, int64_t out_spatial_size,
+                                        int filter_size, int filter_stride, const float *in, int64_t ld_in, float *out,
+                                        int64_t ld_out, const float *weight, const float *packed, int n_in, int n_out,
+                                        int precision, void *stream);
+
+/* *_backward replace the matching upstream *_backward. d_in may be NULL (input needs no gradient); d_weight may be
+ * NULL. `packed_t` = mopa_scn_packWeights(weight, transpose=1 [, flip=1 for submanifold]). d_weight (volume, nIn, nOut)
+ * is OVERWRITTEN (deterministic two-stage reduction; autograd accumulates). workspace: device scratch of at least
+ * mopa_scn_backwardWorkspaceBytes(...) bytes. */
+size_t mopa_scn_backwardWorkspaceBytes(int volume, int n_in, int n_out, int64_t n_rules);
+int mopa_scn_SubmanifoldConvolution_backward(mopa_scn_metadata *m, int64_t spatial_size, int filter_size,
+                                             const float *in, int64_t ld_in, float *d_in, int64_t ld_din,
+                                             const float *d_out, int64_t ld_dout, const float *weight,
+                                             const float *packed_t, float *d_weight, int n_in, int n_out,
+                                             int precision, void *workspace, size_t workspace_bytes, void *stream);
+int mopa_scn_Convolution_backward(mopa_scn_metadata *m, int64_t in_spatial_size, int64_t out_spatial_size,
+                                  int filter_size, int filter_stride, const float *in, int64_t ld_in, float *d_in,
+                                  int64_t ld_din, const float *d_out, int64_t ld_dout, const float *weight,
+                                  const float *packed_t, float *d_weight, int n_in, int n_out, int precision,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+int mopa_scn_Deconvolution_backward(mopa_scn_metadata *m, int64_t in_spatial_size, int64_t out_spatial_size,
+                                    int filter_size, int filter_stride, const float *in, int64_t ld_in, float *d_in,
+                                    int64_t ld_din, const float *d_out, int64_t ld_dout, const float *weight,
+                                    const float *packed_t, float *d_weight, int n_in, int n_out, int precision,
+                                    void *workspace, size_t workspace_bytes, void *stream);
+/* rule count of a prepared rulebook (host value), for sizing the backward workspace; -1 if not built */
+int64_t mopa_scn_Metadata_getSubmanifoldRuleCount(mopa_scn_metadata *m, int64_t spatial_size);
+
+/* ---- BatchNormalization (+ leaky ReLU) -------------------------------------------------------------------------
+ * replaces BatchNormalization_updateOutput / _backward ([UPSTREAM] CUDA/BatchNormalization.cu): per-plane statistics
+ * over the n_active rows; eps inside the sqrt; `momentum` is the KEEP fraction of the running stats (0.9);
+ * running_var uses the unbiased estimate; out = y > 0 ? y : leakiness * y. workspace: >= mopa_scn_bnWorkspaceBytes. */
+size_t mopa_scn_bnWorkspaceBytes(int planes);
+int mopa_scn_BatchNormalization_updateOutput(const float *in, int64_t ld_in, float *out, int64_t ld_out,
+                                             float *save_mean, float *save_invstd, float *running_mean,
+                                             float *running_var, const float *weight, const float *bias, float eps,
+                                             float momentum, int train, float leakiness, int64_t n_active, int planes,
+                                             void *workspace, size_t workspace_bytes, void *stream);
+int mopa_scn_BatchNormalization_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din,
+                                         const float *d_out, int64_t ld_dout, const float *save_mean,
+                                         const float *save_invstd, const float *weight, const float *bias,
+                                         float *d_weight, float *d_bias, float leakiness, int train, int64_t n_active,
+                                         int planes, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- instrumentation: number of kernels this library has launched in this process (bench.py `gpu_launches`) --- */
+int64_t mopa_scn_kernelLaunchCount(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOPA_SCN_H_ */

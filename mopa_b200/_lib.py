@@ -1,0 +1,97 @@
+"""ctypes binding of libmopa_scn.so (the C ABI declared in include/mopa_scn.h).
+
+There is NO CPU fallback: if the library is missing or an entry point fails, the call raises. The prototypes below
+are the single source of truth for the Python side; tests/test_abi.py checks them against the header.
+"""
+import ctypes
+import os
+
+from . import _build
+
+_c = ctypes
+_p = _c.c_void_p
+_i64 = _c.c_int64
+_int = _c.c_int
+_f = _c.c_float
+_sz = _c.c_size_t
+
+PREC_FP32 = 0
+PREC_TF32 = 1
+
+# name -> (restype, argtypes); order and types mirror include/mopa_scn.h
+PROTOTYPES = {
+    "mopa_scn_abi_version": (_int, []),
+    "mopa_scn_last_error": (_c.c_char_p, []),
+    "mopa_scn_Metadata_new": (_p, [_int, _int]),
+    "mopa_scn_Metadata_delete": (None, [_p]),
+    "mopa_scn_InputLayer_setLocations": (_int, [_p, _i64, _p, _i64, _int, _int, _int, _p, _c.POINTER(_i64)]),
+    "mopa_scn_InputLayer_updateOutput": (_int, [_p, _p, _i64, _int, _p, _i64, _p]),
+    "mopa_scn_InputLayer_updateGradInput": (_int, [_p, _p, _i64, _p, _i64, _int, _p]),
+    "mopa_scn_OutputLayer_updateOutput": (_int, [_p, _p, _i64, _int, _p, _i64, _p]),
+    "mopa_scn_OutputLayer_updateGradInput": (_int, [_p, _p, _i64, _p, _i64, _int, _p]),
+    "mopa_scn_Metadata_prepareSubmanifold": (_int, [_p, _i64, _int, _p, _c.POINTER(_i64)]),
+    "mopa_scn_Metadata_prepareConvolution": (_int, [_p, _i64, _i64, _int, _int, _p, _c.POINTER(_i64)]),
+    "mopa_scn_Metadata_getNActive": (_i64, [_p, _i64]),
+    "mopa_scn_Metadata_getNPoints": (_i64, [_p]),
+    "mopa_scn_Metadata_getSpatialLocations": (_int, [_p, _i64, _p]),
+    "mopa_scn_Metadata_getPointToVoxel": (_int, [_p, _p]),
+    "mopa_scn_Metadata_getInputRules": (_int, [_p, _p, _p]),
+    "mopa_scn_Metadata_getSubmanifoldRuleBook": (_int, [_p, _i64, _p, _p]),
+    "mopa_scn_Metadata_getConvolutionRuleBook": (_int, [_p, _i64, _p, _p]),
+    "mopa_scn_packedWeightFloats": (_i64, [_int, _int, _int, _int]),
+    "mopa_scn_packWeights": (_int, [_p, _int, _int, _int, _int, _int, _int, _p, _p]),
+    "mopa_scn_SubmanifoldConvolution_updateOutput": (_int, [_p, _i64, _int, _p, _i64, _p, _i64, _p, _p, _int, _int, _int, _p]),
+    "mopa_scn_Convolution_updateOutput": (_int, [_p, _i64, _i64, _int, _int, _p, _i64, _p, _i64, _p, _p, _int, _int, _int, _p]),
+    "mopa_scn_Deconvolution_updateOutput": (_int, [_p, _i64, _i64, _int, _int, _p, _i64, _p, _i64, _p, _p, _int, _int, _int, _p]),
+    "mopa_scn_backwardWorkspaceBytes": (_sz, [_int, _int, _int, _i64]),
+    "mopa_scn_SubmanifoldConvolution_backward": (_int, [_p, _i64, _int, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _int, _int, _int, _p, _sz, _p]),
+    "mopa_scn_Convolution_backward": (_int, [_p, _i64, _i64, _int, _int, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _int, _int, _int, _p, _sz, _p]),
+    "mopa_scn_Deconvolution_backward": (_int, [_p, _i64, _i64, _int, _int, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _int, _int, _int, _p, _sz, _p]),
+    "mopa_scn_Metadata_getSubmanifoldRuleCount": (_i64, [_p, _i64]),
+    "mopa_scn_bnWorkspaceBytes": (_sz, [_int]),
+    "mopa_scn_BatchNormalization_updateOutput": (_int, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _f, _f, _int, _f, _i64, _int, _p, _sz, _p]),
+    "mopa_scn_BatchNormalization_backward": (_int, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _f, _int, _i64, _int, _p, _sz, _p]),
+    "mopa_scn_kernelLaunchCount": (_i64, []),
+}
+
+_lib = None
+
+
+class ScnError(RuntimeError):
+    pass
+
+
+def library_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building in-tree first if the .so is absent or stale and nvcc exists). Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path) or _build.stale():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this box and no prebuilt library
+            if not os.path.exists(path):
+                raise ScnError("libmopa_scn.so is missing and could not be built (%s); mopa_b200 has no CPU fallback" % e)
+    lib = _c.CDLL(path)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mopa_scn_abi_version() != 1:
+        raise ScnError("libmopa_scn.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        raise ScnError(load().mopa_scn_last_error().decode("utf-8", "replace"))
+
+
+def kernel_launches():
+    return int(load().mopa_scn_kernelLaunchCount())

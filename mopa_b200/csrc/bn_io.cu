@@ -1,0 +1,426 @@
+// BatchNorm(+leaky ReLU) and the Input/Output layer feature kernels.
+// Replaces [UPSTREAM] SparseConvNet SCN/CUDA/{BatchNormalization,IOLayers}.cu, reached from
+// mopa/models/scn_unet.py:26,29,30 and from scn.UNet's BatchNormLeakyReLU layers.
+// All of these are pure HBM streaming kernels: 128-bit accesses along the plane axis, grid sized from the SM count,
+// per-block partial statistics combined in fixed order by the last block to finish (deterministic, no float atomics).
+#include "geometry.cuh"
+#include "mopa_scn.h"
+
+namespace mopa {
+
+// ------------------------------------------------------------------------------------------------ BatchNorm
+constexpr int kBnMaxBlocks = 4 * kNumSMs;
+// workspace layout (floats): [0] block counter (int), [8 .. 8+2C) fused scale/shift or gradMean/k, then partials
+__host__ __device__ inline size_t bn_ws_floats(int planes) { return 8 + 2 * (size_t)planes + (size_t)kBnMaxBlocks * 2 * planes; }
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+    using T = float4;
+    static __device__ __forceinline__ void get(const float *p, float (&v)[4]) {
+        float4 x = *reinterpret_cast<const float4 *>(p);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    }
+    static __device__ __forceinline__ void put(float *p, const float (&v)[4]) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <>
+struct Vec<1> {
+    static __device__ __forceinline__ void get(const float *p, float (&v)[1]) { v[0] = *p; }
+    static __device__ __forceinline__ void put(float *p, const float (&v)[1]) { *p = v[0]; }
+};
+
+// block = (planes / VEC, rows_per_block). BWD = false: S1 = sum(x - x0), S2 = sum((x - x0)^2)   (x0 = row 0, a shift
+// that keeps the single-pass variance well conditioned). BWD = true: S1 = sum(d), S2 = sum((x - mean) d) with
+// d = d_out masked by the sign of the recomputed output.
+template <int VEC, bool BWD>
+__global__ void __launch_bounds__(256) k_bn_stats(const float *__restrict__ x, int64_t ld_x, const float *__restrict__ dout,
+                                                  int64_t ld_dout, int64_t n, int planes, float *__restrict__ ws,
+                                                  const float *__restrict__ mean_in, const float *__restrict__ invstd_in,
+                                                  const float *__restrict__ weight, const float *__restrict__ bias,
+                                                  float leakiness, int train, float eps, float momentum,
+                                                  float *__restrict__ save_mean, float *__restrict__ save_invstd,
+                                                  float *__restrict__ running_mean, float *__restrict__ running_var,
+                                                  float *__restrict__ d_weight, float *__restrict__ d_bias) {
+    extern __shared__ float sred[];  // [blockDim.y][2 * planes]
+    const int c0 = threadIdx.x * VEC;
+    float s1[VEC], s2[VEC], ref[VEC], sc[VEC], sh[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        s1[e] = s2[e] = 0.f;
+        if (BWD) {
+            ref[e] = mean_in[c0 + e];
+            sc[e] = invstd_in[c0 + e] * weight[c0 + e];
+            sh[e] = bias[c0 + e] - ref[e] * sc[e];
+        } else {
+            ref[e] = x[c0 + e];
+        }
+    }
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; r < n; r += (int64_t)gridDim.x * blockDim.y) {
+        float v[VEC];
+        Vec<VEC>::get(x + r * ld_x + c0, v);
+        if (BWD) {
+            float d[VEC];
+            Vec<VEC>::get(dout + r * ld_dout + c0, d);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const float y = fmaf(v[e], sc[e], sh[e]);
+                const float dm = y > 0.f ? d[e] : d[e] * leakiness;
+                s1[e] += dm;
+                s2[e] = fmaf(v[e] - ref[e], dm, s2[e]);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const float dv = v[e] - ref[e];
+                s1[e] += dv;
+                s2[e] = fmaf(dv, dv, s2[e]);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        sred[threadIdx.y * 2 * planes + c0 + e] = s1[e];
+        sred[threadIdx.y * 2 * planes + planes + c0 + e] = s2[e];
+    }
+    __syncthreads();
+    float *partial = ws + 8 + 2 * planes;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    for (int i = tid; i < 2 * planes; i += nthr) {
+        float s = 0.f;
+        for (int y = 0; y < (int)blockDim.y; ++y) s += sred[y * 2 * planes + i];
+        partial[(int64_t)blockIdx.x * 2 * planes + i] = s;
+    }
+    // ---- last block to finish combines the partials in block order
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        int *counter = reinterpret_cast<int *>(ws);
+        const int done = atomicAdd(counter, 1);
+        is_last = done == (int)gridDim.x - 1;
+        if (is_last) *counter = 0;  // leave the workspace zeroed for the next call
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int c = tid; c < planes; c += nthr) {
+        double a = 0.0, b = 0.0;
+        for (int blk = 0; blk < (int)gridDim.x; ++blk) {
+            a += (double)__ldcg(partial + (int64_t)blk * 2 * planes + c);
+            b += (double)__ldcg(partial + (int64_t)blk * 2 * planes + planes + c);
+        }
+        const double dn = (double)n;
+        if (!BWD) {
+            const double shift = (double)x[c];
+            const double mean = shift + a / dn;
+            double m2 = b - a * a / dn;  // sum (x - mean)^2
+            if (m2 < 0.0) m2 = 0.0;
+            const float invstd = (float)(1.0 / sqrt(m2 / dn + (double)eps));
+            save_mean[c] = (float)mean;
+            save_invstd[c] = invstd;
+            running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * (float)mean;
+            running_var[c] = momentum * running_var[c] + (1.f - momentum) * (float)(m2 / (n > 1 ? dn - 1.0 : 1.0));
+        } else {
+            const float invstd = invstd_in[c];
+            if (d_weight) d_weight[c] = (float)(b * (double)invstd);
+            if (d_bias) d_bias[c] = (float)a;
+            ws[8 + c] = train ? (float)(a / dn) : 0.f;                                          // gradMean
+            ws[8 + planes + c] = train ? (float)(b * (double)invstd * (double)invstd / dn) : 0.f;  // k
+        }
+    }
+}
+
+__global__ void k_bn_eval_stats(const float *__restrict__ running_mean, const float *__restrict__ running_var, float eps,
+                                int planes, float *__restrict__ save_mean, float *__restrict__ save_invstd) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= planes) return;
+    save_mean[c] = running_mean[c];
+    save_invstd[c] = 1.f / sqrtf(running_var[c] + eps);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_bn_apply(const float *__restrict__ x, int64_t ld_x, float *__restrict__ out,
+                                                  int64_t ld_out, int64_t n, int planes, const float *__restrict__ mean,
+                                                  const float *__restrict__ invstd, const float *__restrict__ weight,
+                                                  const float *__restrict__ bias, float leakiness) {
+    const int c0 = threadIdx.x * VEC;
+    float sc[VEC], sh[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        sc[e] = invstd[c0 + e] * weight[c0 + e];
+        sh[e] = bias[c0 + e] - mean[c0 + e] * sc[e];
+    }
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; r < n; r += (int64_t)gridDim.x * blockDim.y) {
+        float v[VEC];
+        Vec<VEC>::get(x + r * ld_x + c0, v);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const float y = fmaf(v[e], sc[e], sh[e]);
+            v[e] = y > 0.f ? y : y * leakiness;
+        }
+        Vec<VEC>::put(out + r * ld_out + c0, v);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float *__restrict__ x, int64_t ld_x,
+                                                      const float *__restrict__ dout, int64_t ld_dout,
+                                                      float *__restrict__ din, int64_t ld_din, int64_t n, int planes,
+                                                      const float *__restrict__ mean, const float *__restrict__ invstd,
+                                                      const float *__restrict__ weight, const float *__restrict__ bias,
+                                                      const float *__restrict__ ws, float leakiness) {
+    const int c0 = threadIdx.x * VEC;
+    float sc[VEC], sh[VEC], mu[VEC], gm[VEC], kk[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        mu[e] = mean[c0 + e];
+        sc[e] = invstd[c0 + e] * weight[c0 + e];
+        sh[e] = bias[c0 + e] - mu[e] * sc[e];
+        gm[e] = ws[8 + c0 + e];
+        kk[e] = ws[8 + planes + c0 + e];
+    }
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; r < n; r += (int64_t)gridDim.x * blockDim.y) {
+        float v[VEC], d[VEC];
+        Vec<VEC>::get(x + r * ld_x + c0, v);
+        Vec<VEC>::get(dout + r * ld_dout + c0, d);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const float y = fmaf(v[e], sc[e], sh[e]);
+            const float dm = y > 0.f ? d[e] : d[e] * leakiness;
+            v[e] = (dm - gm[e] - (v[e] - mu[e]) * kk[e]) * sc[e];
+        }
+        Vec<VEC>::put(din + r * ld_din + c0, v);
+    }
+}
+
+struct BnShape {
+    int vec;
+    dim3 block;
+    unsigned grid;
+    size_t smem;
+};
+static BnShape bn_shape(int64_t n, int planes, bool vec_ok) {
+    BnShape s;
+    s.vec = (vec_ok && planes % 4 == 0) ? 4 : 1;
+    int tx = planes / s.vec;
+    int ty = 256 / tx;
+    if (ty < 1) ty = 1;
+    if (ty > 64) ty = 64;
+    s.block = dim3(tx, ty);
+    int64_t want = ceil_div(n > 0 ? n : 1, (int64_t)ty * 4);  // >= 4 rows per thread
+    s.grid = (unsigned)(want < 1 ? 1 : (want > kBnMaxBlocks ? kBnMaxBlocks : want));
+    s.smem = (size_t)ty * 2 * planes * 4;
+    return s;
+}
+static bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+// ------------------------------------------------------------------------------------------------ IO layers
+// InputLayer mode 4: out[v][c] = sum over the voxel's rows, ascending, of (1/n_v) * in[row][c]  (multiply, then add)
+__global__ void __launch_bounds__(256) k_pool_fwd(const float *__restrict__ in, int64_t ld_in, int planes,
+                                                  const int32_t *__restrict__ off, const int32_t *__restrict__ rows,
+                                                  int64_t V, float *__restrict__ out, int64_t ld_out) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= V * planes) return;
+    const int64_t v = idx / planes;
+    const int c = (int)(idx - v * planes);
+    const int beg = off[v], end = off[v + 1];
+    const float inv = 1.f / (float)(end - beg);
+    float acc = 0.f;
+    for (int j = beg; j < end; ++j) acc = __fadd_rn(acc, __fmul_rn(in[(int64_t)rows[j] * ld_in + c], inv));
+    out[v * ld_out + c] = acc;
+}
+__global__ void __launch_bounds__(256) k_pool_bwd(float *__restrict__ din, int64_t ld_din, int planes,
+                                                  const int32_t *__restrict__ off, const int32_t *__restrict__ p2v,
+                                                  int64_t n, const float *__restrict__ dout, int64_t ld_dout) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * planes) return;
+    const int64_t i = idx / planes;
+    const int c = (int)(idx - i * planes);
+    const int v = p2v[i];
+    const float inv = 1.f / (float)(off[v + 1] - off[v]);
+    din[i * ld_din + c] = __fmul_rn(dout[(int64_t)v * ld_dout + c], inv);
+}
+// OutputLayer: out[i] = in[voxel(i)]; one thread moves VEC planes
+template <int VEC>
+__global__ void __launch_bounds__(256) k_unpool_fwd(const float *__restrict__ in, int64_t ld_in, int planes,
+                                                    const int32_t *__restrict__ p2v, int64_t n, float *__restrict__ out,
+                                                    int64_t ld_out) {
+    const int per_row = planes / VEC;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * per_row) return;
+    const int64_t i = idx / per_row;
+    const int c = (int)(idx - i * per_row) * VEC;
+    float v[VEC];
+    Vec<VEC>::get(in + (int64_t)p2v[i] * ld_in + c, v);
+    Vec<VEC>::put(out + i * ld_out + c, v);
+}
+template <int VEC>
+__global__ void __launch_bounds__(256) k_unpool_bwd(float *__restrict__ din, int64_t ld_din, int planes,
+                                                    const int32_t *__restrict__ off, const int32_t *__restrict__ rows,
+                                                    int64_t V, const float *__restrict__ dout, int64_t ld_dout) {
+    const int per_row = planes / VEC;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= V * per_row) return;
+    const int64_t v = idx / per_row;
+    const int c = (int)(idx - v * per_row) * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+    for (int j = off[v]; j < off[v + 1]; ++j) {
+        float d[VEC];
+        Vec<VEC>::get(dout + (int64_t)rows[j] * ld_dout + c, d);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = __fadd_rn(acc[e], d[e]);
+    }
+    Vec<VEC>::put(din + v * ld_din + c, acc);
+}
+
+}  // namespace mopa
+
+using namespace mopa;
+
+extern "C" {
+
+size_t mopa_scn_bnWorkspaceBytes(int planes) { return bn_ws_floats(planes) * 4; }
+
+int mopa_scn_BatchNormalization_updateOutput(const float *in, int64_t ld_in, float *out, int64_t ld_out,
+                                             float *save_mean, float *save_invstd, float *running_mean,
+                                             float *running_var, const float *weight, const float *bias, float eps,
+                                             float momentum, int train, float leakiness, int64_t n_active, int planes,
+                                             void *workspace, size_t workspace_bytes, void *stream) {
+    MOPA_CHECK(planes > 0 && planes <= 1024, "BatchNormalization: planes out of range");
+    MOPA_CHECK(workspace && workspace_bytes >= mopa_scn_bnWorkspaceBytes(planes), "BatchNormalization: workspace too small");
+    MOPA_CHECK(weight && bias, "BatchNormalization: affine parameters are required");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_active == 0) return 0;
+    const bool vec_ok = al16(in) && al16(out) && ld_in % 4 == 0 && ld_out % 4 == 0;
+    BnShape sh = bn_shape(n_active, planes, vec_ok);
+    float *ws = reinterpret_cast<float *>(workspace);
+    if (train) {
+        if (sh.vec == 4)
+            k_bn_stats<4, false><<<sh.grid, sh.block, sh.smem, s>>>(in, ld_in, nullptr, 0, n_active, planes, ws, nullptr,
+                                                                    nullptr, nullptr, nullptr, leakiness, 1, eps, momentum,
+                                                                    save_mean, save_invstd, running_mean, running_var,
+                                                                    nullptr, nullptr);
+        else
+            k_bn_stats<1, false><<<sh.grid, sh.block, sh.smem, s>>>(in, ld_in, nullptr, 0, n_active, planes, ws, nullptr,
+                                                                    nullptr, nullptr, nullptr, leakiness, 1, eps, momentum,
+                                                                    save_mean, save_invstd, running_mean, running_var,
+                                                                    nullptr, nullptr);
+    } else {
+        k_bn_eval_stats<<<(unsigned)ceil_div(planes, 128), 128, 0, s>>>(running_mean, running_var, eps, planes, save_mean,
+                                                                        save_invstd);
+    }
+    MOPA_LAUNCHED();
+    if (sh.vec == 4)
+        k_bn_apply<4><<<sh.grid, sh.block, 0, s>>>(in, ld_in, out, ld_out, n_active, planes, save_mean, save_invstd, weight,
+                                                   bias, leakiness);
+    else
+        k_bn_apply<1><<<sh.grid, sh.block, 0, s>>>(in, ld_in, out, ld_out, n_active, planes, save_mean, save_invstd, weight,
+                                                   bias, leakiness);
+    MOPA_LAUNCHED();
+    return 0;
+}
+
+int mopa_scn_BatchNormalization_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din,
+                                         const float *d_out, int64_t ld_dout, const float *save_mean,
+                                         const float *save_invstd, const float *weight, const float *bias,
+                                         float *d_weight, float *d_bias, float leakiness, int train, int64_t n_active,
+                                         int planes, void *workspace, size_t workspace_bytes, void *stream) {
+    MOPA_CHECK(planes > 0 && planes <= 1024, "BatchNormalization: planes out of range");
+    MOPA_CHECK(workspace && workspace_bytes >= mopa_scn_bnWorkspaceBytes(planes), "BatchNormalization: workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_active == 0) {
+        if (d_weight) MOPA_CUDA(cudaMemsetAsync(d_weight, 0, (size_t)planes * 4, s));
+        if (d_bias) MOPA_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)planes * 4, s));
+        return 0;
+    }
+    const bool vec_ok = al16(in) && al16(d_in) && al16(d_out) && ld_in % 4 == 0 && ld_din % 4 == 0 && ld_dout % 4 == 0;
+    BnShape sh = bn_shape(n_active, planes, vec_ok);
+    float *ws = reinterpret_cast<float *>(workspace);
+    if (sh.vec == 4)
+        k_bn_stats<4, true><<<sh.grid, sh.block, sh.smem, s>>>(in, ld_in, d_out, ld_dout, n_active, planes, ws, save_mean,
+                                                               save_invstd, weight, bias, leakiness, train, 0.f, 0.f,
+                                                               nullptr, nullptr, nullptr, nullptr, d_weight, d_bias);
+    else
+        k_bn_stats<1, true><<<sh.grid, sh.block, sh.smem, s>>>(in, ld_in, d_out, ld_dout, n_active, planes, ws, save_mean,
+                                                               save_invstd, weight, bias, leakiness, train, 0.f, 0.f,
+                                                               nullptr, nullptr, nullptr, nullptr, d_weight, d_bias);
+    MOPA_LAUNCHED();
+    if (d_in) {
+        if (sh.vec == 4)
+            k_bn_bwd_apply<4><<<sh.grid, sh.block, 0, s>>>(in, ld_in, d_out, ld_dout, d_in, ld_din, n_active, planes,
+                                                           save_mean, save_invstd, weight, bias, ws, leakiness);
+        else
+            k_bn_bwd_apply<1><<<sh.grid, sh.block, 0, s>>>(in, ld_in, d_out, ld_dout, d_in, ld_din, n_active, planes,
+                                                           save_mean, save_invstd, weight, bias, ws, leakiness);
+        MOPA_LAUNCHED();
+    }
+    return 0;
+}
+
+static int io_check(mopa_scn_metadata *m, int planes) {
+    MOPA_CHECK(m != nullptr && !m->levels.empty(), "metadata has no input layer");
+    MOPA_CHECK(planes > 0, "planes must be positive");
+    MOPA_CUDA(cudaSetDevice(m->device));
+    return 0;
+}
+
+int mopa_scn_InputLayer_updateOutput(mopa_scn_metadata *m, const float *in, int64_t ld_in, int planes, float *out,
+                                     int64_t ld_out, void *stream) {
+    MOPA_TRY(io_check(m, planes));
+    const int64_t V = m->levels[0].V;
+    if (V == 0) return 0;
+    k_pool_fwd<<<(unsigned)ceil_div(V * planes, 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, planes, m->csr_off,
+                                                                                      m->csr_rows, V, out, ld_out);
+    MOPA_LAUNCHED();
+    return 0;
+}
+
+int mopa_scn_InputLayer_updateGradInput(mopa_scn_metadata *m, float *d_in, int64_t ld_din, const float *d_out,
+                                        int64_t ld_dout, int planes, void *stream) {
+    MOPA_TRY(io_check(m, planes));
+    const int64_t n = m->n_points;
+    if (n == 0) return 0;
+    k_pool_bwd<<<(unsigned)ceil_div(n * planes, 256), 256, 0, (cudaStream_t)stream>>>(d_in, ld_din, planes, m->csr_off,
+                                                                                      m->p2v, n, d_out, ld_dout);
+    MOPA_LAUNCHED();
+    return 0;
+}
+
+int mopa_scn_OutputLayer_updateOutput(mopa_scn_metadata *m, const float *in, int64_t ld_in, int planes, float *out,
+                                      int64_t ld_out, void *stream) {
+    MOPA_TRY(io_check(m, planes));
+    const int64_t n = m->n_points;
+    if (n == 0) return 0;
+    const bool v4 = planes % 4 == 0 && al16(in) && al16(out) && ld_in % 4 == 0 && ld_out % 4 == 0;
+    if (v4)
+        k_unpool_fwd<4><<<(unsigned)ceil_div(n * (planes / 4), 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, planes, m->p2v,
+                                                                                                     n, out, ld_out);
+    else
+        k_unpool_fwd<1><<<(unsigned)ceil_div(n * planes, 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, planes, m->p2v, n,
+                                                                                               out, ld_out);
+    MOPA_LAUNCHED();
+    return 0;
+}
+
+int mopa_scn_OutputLayer_updateGradInput(mopa_scn_metadata *m, float *d_in, int64_t ld_din, const float *d_out,
+                                         int64_t ld_dout, int planes, void *stream) {
+    MOPA_TRY(io_check(m, planes));
+    const int64_t V = m->levels[0].V;
+    if (V == 0) return 0;
+    const bool v4 = planes % 4 == 0 && al16(d_in) && al16(d_out) && ld_din % 4 == 0 && ld_dout % 4 == 0;
+    if (v4)
+        k_unpool_bwd<4><<<(unsigned)ceil_div(V * (planes / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+            d_in, ld_din, planes, m->csr_off, m->csr_rows, V, d_out, ld_dout);
+    else
+        k_unpool_bwd<1><<<(unsigned)ceil_div(V * planes, 256), 256, 0, (cudaStream_t)stream>>>(
+            d_in, ld_din, planes, m->csr_off, m->csr_rows, V, d_out, ld_dout);
+    MOPA_LAUNCHED();
+    return 0;
+}
+
+}  // extern "C"

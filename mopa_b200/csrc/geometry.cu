@@ -1,0 +1,658 @@
+// Coordinate hashing, voxelisation and rulebook construction on the GPU.
+//
+// Replaces, for the path mopa/models/scn_unet.py:25-30 reaches, the host-side code of [UPSTREAM] SparseConvNet
+// SCN/Metadata/{Metadata.cpp, IOLayersRules.h, SubmanifoldConvolutionRules.h, ConvolutionRules.h}. Upstream builds
+// google::dense_hash_map grids and std::vector rulebooks on the CPU every forward; here every grid is an
+// open-addressing table in HBM and every "rulebook" is a dense (offset, out-row) -> in-row table that the conv
+// kernels read coalesced. All of it is integer work; results are bit-exact against oracle/scn_oracle.py.
+//
+// Voxel numbering: level-0 ids = order of first occurrence among the input rows; coarse ids =
+// order of first occurrence when scanning fine ids ascending. Both come from one routine, unique_first():
+//   insert all keys (atomicCAS) and atomicMin the element index into the slot  -> slot holds the first index
+//   flag elements that ARE their slot's first index, exclusive-scan the flags  -> rank = id
+//   write id back into the slot, then every element reads its id from its slot.
+#include <mutex>
+
+#include "geometry.cuh"
+#include "mopa_scn.h"
+
+namespace mopa {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+// ------------------------------------------------------------------------------------------------ allocation
+int meta_alloc(mopa_scn_metadata *m, void **p, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) bytes = 16;
+    MOPA_CUDA(cudaMallocAsync(p, bytes, s));
+    m->allocs.push_back(*p);
+    return 0;
+}
+
+static int tmp_alloc(void **p, size_t bytes, cudaStream_t s) {
+    MOPA_CUDA(cudaMallocAsync(p, bytes ? bytes : 16, s));
+    return 0;
+}
+
+// pinned 256-byte staging blocks, recycled process-wide (cudaHostAlloc costs tens of microseconds)
+static std::mutex g_pin_mu;
+static std::vector<int32_t *> g_pin_free;
+static int32_t *pin_get() {
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        if (!g_pin_free.empty()) {
+            int32_t *p = g_pin_free.back();
+            g_pin_free.pop_back();
+            return p;
+        }
+    }
+    int32_t *p = nullptr;
+    if (cudaHostAlloc((void **)&p, 256, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+static void pin_put(int32_t *p) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pin_free.push_back(p);
+}
+
+// ------------------------------------------------------------------------------------------------ scan
+__device__ __forceinline__ int block_exclusive_scan_1024(int v, int *total) {
+    __shared__ int warp_sums[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    __syncthreads();  // protect warp_sums from the previous call
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int s = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+        int si = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, si, d);
+            if (lane >= d) si += t;
+        }
+        warp_sums[lane] = si - s;
+        if (lane == 31 && total) *total = si;
+    }
+    __syncthreads();
+    return incl - v + warp_sums[w];
+}
+
+__global__ void __launch_bounds__(1024) k_scan_blocks(const int32_t *__restrict__ in, int32_t *__restrict__ out,
+                                                      int64_t n, int32_t *__restrict__ bsum) {
+    __shared__ int tot;
+    int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    int v = i < n ? in[i] : 0;
+    int e = block_exclusive_scan_1024(v, &tot);
+    if (i < n) out[i] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan of bsum[0..nb) in place, grand total to *total
+__global__ void __launch_bounds__(1024) k_scan_sums(int32_t *__restrict__ bsum, int64_t nb, int32_t *__restrict__ total) {
+    __shared__ int tot;
+    int carry = 0;
+    for (int64_t base = 0; base < nb; base += 1024) {
+        int64_t i = base + threadIdx.x;
+        int v = i < nb ? bsum[i] : 0;
+        int e = block_exclusive_scan_1024(v, &tot);
+        if (i < nb) bsum[i] = e + carry;
+        __syncthreads();
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_add(int32_t *__restrict__ out, int64_t n, const int32_t *__restrict__ bsum) {
+    int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    if (i < n) out[i] += bsum[blockIdx.x];
+}
+
+// exclusive scan of int32; `bsum` scratch of ceil(n/1024) ints; total (device) may be null
+static int exclusive_scan(const int32_t *in, int32_t *out, int64_t n, int32_t *bsum, int32_t *total, cudaStream_t s) {
+    if (n <= 0) {
+        if (total) MOPA_CUDA(cudaMemsetAsync(total, 0, 4, s));
+        return 0;
+    }
+    int64_t nb = ceil_div(n, 1024);
+    k_scan_blocks<<<(unsigned)nb, 1024, 0, s>>>(in, out, n, bsum);
+    MOPA_LAUNCHED();
+    k_scan_sums<<<1, 1024, 0, s>>>(bsum, nb, total);
+    MOPA_LAUNCHED();
+    if (nb > 1) {
+        k_scan_add<<<(unsigned)nb, 1024, 0, s>>>(out, n, bsum);
+        MOPA_LAUNCHED();
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ unique_first
+// MODE 0: keys from an int64 (n, ncols) coordinate matrix (validated); MODE 1: stride-2 parents of fine keys.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_insert(const int64_t *__restrict__ coords, int ncols, int64_t spatial,
+                                                const uint64_t *__restrict__ fine_keys, int64_t n,
+                                                uint64_t *__restrict__ tab_keys, int32_t *__restrict__ tab_vals,
+                                                uint32_t mask, int32_t *__restrict__ slot_of,
+                                                uint64_t *__restrict__ key_of, int32_t *__restrict__ kidx,
+                                                int32_t *__restrict__ err) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key;
+    if (MODE == 0) {
+        int64_t x, y, z, b = 0;
+        if (ncols == 4) {
+            const longlong2 *row = reinterpret_cast<const longlong2 *>(coords + 4 * i);
+            longlong2 a = __ldg(row), c = __ldg(row + 1);
+            x = a.x; y = a.y; z = c.x; b = c.y;
+        } else {
+            x = coords[3 * i]; y = coords[3 * i + 1]; z = coords[3 * i + 2];
+        }
+        if (x < 0 || y < 0 || z < 0 || x >= spatial || y >= spatial || z >= spatial || b < 0 || b >= 65535) {
+            atomicExch(err, 1);
+            slot_of[i] = -1;
+            key_of[i] = kEmptyKey;
+            return;
+        }
+        key = pack_key((uint32_t)x, (uint32_t)y, (uint32_t)z, (uint32_t)b);
+    } else {
+        uint64_t fk = fine_keys[i];
+        key = parent_key(fk);
+        // filter position of the fine site inside its 2x2x2 parent: (x&1)*4 + (y&1)*2 + (z&1)
+        kidx[i] = (int)(((fk >> 32) & 1) * 4 + ((fk >> 16) & 1) * 2 + (fk & 1));
+    }
+    uint32_t s = hash_key(key) & mask;
+    while (true) {
+        uint64_t cur = tab_keys[s];
+        if (cur == key) break;
+        if (cur == kEmptyKey) {
+            unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(tab_keys + s),
+                                                (unsigned long long)kEmptyKey, (unsigned long long)key);
+            if (prev == kEmptyKey || prev == key) break;
+        }
+        s = (s + 1) & mask;
+    }
+    atomicMin(tab_vals + s, (int32_t)i);
+    slot_of[i] = (int32_t)s;
+    key_of[i] = key;
+}
+
+__global__ void __launch_bounds__(256) k_flag_first(const int32_t *__restrict__ slot_of,
+                                                    const int32_t *__restrict__ tab_vals, int64_t n,
+                                                    int32_t *__restrict__ flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int s = slot_of[i];
+    flags[i] = (s >= 0 && tab_vals[s] == (int32_t)i) ? 1 : 0;
+}
+
+// elements that are a first occurrence publish their id into the slot and their key into the id-ordered key list
+__global__ void __launch_bounds__(256) k_assign_ids(const int32_t *__restrict__ slot_of,
+                                                    const int32_t *__restrict__ flags,
+                                                    const int32_t *__restrict__ rank,
+                                                    const uint64_t *__restrict__ key_of, int64_t n,
+                                                    int32_t *__restrict__ tab_vals, uint64_t *__restrict__ uniq_keys) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flags[i]) return;
+    int id = rank[i];
+    tab_vals[slot_of[i]] = id;
+    uniq_keys[id] = key_of[i];
+}
+
+__global__ void __launch_bounds__(256) k_read_ids(const int32_t *__restrict__ slot_of,
+                                                  const int32_t *__restrict__ tab_vals, int64_t n,
+                                                  int32_t *__restrict__ ids, int32_t *__restrict__ counts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int s = slot_of[i];
+    int id = s >= 0 ? tab_vals[s] : -1;
+    ids[i] = id;
+    if (counts && id >= 0) atomicAdd(counts + id, 1);
+}
+
+static uint32_t table_capacity(int64_t n) {
+    uint64_t cap = 1024;
+    while (cap < (uint64_t)(2 * n + 2)) cap <<= 1;
+    return (uint32_t)cap;
+}
+
+// Builds the table + ids; *count_dev receives the number of unique keys. uniq_keys must hold n entries.
+static int unique_first(int mode, const int64_t *coords, int ncols, int64_t spatial, const uint64_t *fine_keys,
+                        int64_t n, uint64_t *tab_keys, int32_t *tab_vals, uint32_t cap, uint64_t *uniq_keys,
+                        int32_t *ids, int32_t *kidx, int32_t *counts, int32_t *count_dev, int32_t *err_dev,
+                        cudaStream_t s) {
+    MOPA_CUDA(cudaMemsetAsync(tab_keys, 0xFF, (size_t)cap * 8, s));
+    MOPA_CUDA(cudaMemsetAsync(tab_vals, 0x7F, (size_t)cap * 4, s));
+    if (n == 0) {
+        MOPA_CUDA(cudaMemsetAsync(count_dev, 0, 4, s));
+        return 0;
+    }
+    int32_t *slot_of, *flags, *rank, *bsum;
+    uint64_t *key_of;
+    int64_t nb = ceil_div(n, 1024);
+    MOPA_TRY(tmp_alloc((void **)&slot_of, n * 4, s));
+    MOPA_TRY(tmp_alloc((void **)&flags, n * 4, s));
+    MOPA_TRY(tmp_alloc((void **)&rank, n * 4, s));
+    MOPA_TRY(tmp_alloc((void **)&bsum, nb * 4, s));
+    MOPA_TRY(tmp_alloc((void **)&key_of, n * 8, s));
+    unsigned g = (unsigned)ceil_div(n, 256);
+    if (mode == 0)
+        k_insert<0><<<g, 256, 0, s>>>(coords, ncols, spatial, nullptr, n, tab_keys, tab_vals, cap - 1, slot_of, key_of,
+                                      nullptr, err_dev);
+    else
+        k_insert<1><<<g, 256, 0, s>>>(nullptr, 0, 0, fine_keys, n, tab_keys, tab_vals, cap - 1, slot_of, key_of, kidx,
+                                      err_dev);
+    MOPA_LAUNCHED();
+    k_flag_first<<<g, 256, 0, s>>>(slot_of, tab_vals, n, flags);
+    MOPA_LAUNCHED();
+    MOPA_TRY(exclusive_scan(flags, rank, n, bsum, count_dev, s));
+    k_assign_ids<<<g, 256, 0, s>>>(slot_of, flags, rank, key_of, n, tab_vals, uniq_keys);
+    MOPA_LAUNCHED();
+    k_read_ids<<<g, 256, 0, s>>>(slot_of, tab_vals, n, ids, counts);
+    MOPA_LAUNCHED();
+    MOPA_CUDA(cudaFreeAsync(slot_of, s));
+    MOPA_CUDA(cudaFreeAsync(flags, s));
+    MOPA_CUDA(cudaFreeAsync(rank, s));
+    MOPA_CUDA(cudaFreeAsync(bsum, s));
+    MOPA_CUDA(cudaFreeAsync(key_of, s));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ input rules (CSR)
+__global__ void __launch_bounds__(256) k_csr_fill(const int32_t *__restrict__ p2v, const int32_t *__restrict__ off,
+                                                  int64_t n, int32_t *__restrict__ cursor, int32_t *__restrict__ tmp) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int v = p2v[i];
+    if (v < 0) return;
+    int pos = atomicAdd(cursor + v, 1);
+    tmp[off[v] + pos] = (int32_t)i;
+}
+
+// order each voxel's row list ascending: rank of row i = number of rows of the same voxel that are smaller
+__global__ void __launch_bounds__(256) k_csr_order(const int32_t *__restrict__ p2v, const int32_t *__restrict__ off,
+                                                   const int32_t *__restrict__ tmp, int64_t n,
+                                                   int32_t *__restrict__ rows) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int v = p2v[i];
+    if (v < 0) return;
+    int beg = off[v], end = off[v + 1];
+    int r = 0;
+    for (int j = beg; j < end; ++j) r += (tmp[j] < (int32_t)i);
+    rows[beg + r] = (int32_t)i;
+}
+
+__global__ void k_set_last(int32_t *off, int64_t v_bound, const int32_t *count_dev, int32_t n) {
+    // off[V] = n where V = *count_dev
+    (void)v_bound;
+    off[*count_dev] = n;
+}
+
+// ------------------------------------------------------------------------------------------------ submanifold table
+// grid (ceil(V / 256), 27): one thread per (offset, site); writes are coalesced along the site axis.
+__global__ void __launch_bounds__(256) k_subm_table(const uint64_t *__restrict__ keys, int64_t V, int spatial,
+                                                    const uint64_t *__restrict__ tab_keys,
+                                                    const int32_t *__restrict__ tab_vals, uint32_t mask,
+                                                    int32_t *__restrict__ nbr, int64_t ld) {
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= V) return;
+    const int k = blockIdx.y;
+    const int dx = k / 9 - 1, dy = (k / 3) % 3 - 1, dz = k % 3 - 1;
+    int x, y, z, b;
+    unpack_key(keys[o], x, y, z, b);
+    x += dx; y += dy; z += dz;
+    int id = -1;
+    if (k == 13) {
+        id = (int)o;
+    } else if (x >= 0 && y >= 0 && z >= 0 && x < spatial && y < spatial && z < spatial) {
+        uint64_t q = pack_key((uint32_t)x, (uint32_t)y, (uint32_t)z, (uint32_t)b);
+        uint32_t s = hash_key(q) & mask;
+        while (true) {
+            uint64_t cur = __ldg(tab_keys + s);
+            if (cur == q) { id = __ldg(tab_vals + s); break; }
+            if (cur == kEmptyKey) break;
+            s = (s + 1) & mask;
+        }
+    }
+    nbr[(int64_t)k * ld + o] = id;
+}
+
+__global__ void __launch_bounds__(256) k_child_scatter(const int32_t *__restrict__ parent,
+                                                       const int32_t *__restrict__ kidx, int64_t Vf,
+                                                       int32_t *__restrict__ child, int64_t ld) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Vf) return;
+    child[(int64_t)kidx[c] * ld + parent[c]] = (int32_t)c;
+}
+
+// ------------------------------------------------------------------------------------------------ rulebook compaction
+// Warp-cooperative ordered compaction of a dense (K, ld) table into offset-major (in, out) pairs, ascending out row.
+__global__ void __launch_bounds__(1024) k_rule_flags(const int32_t *__restrict__ table, int64_t ld, int64_t V, int K,
+                                                     int32_t *__restrict__ flags) {
+    int64_t o = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    int k = blockIdx.y;
+    if (o < V && k < K) flags[(int64_t)k * V + o] = table[(int64_t)k * ld + o] >= 0;
+}
+__global__ void __launch_bounds__(1024) k_rule_write(const int32_t *__restrict__ table, int64_t ld, int64_t V, int K,
+                                                     const int32_t *__restrict__ rank, int32_t *__restrict__ pairs) {
+    int64_t o = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    int k = blockIdx.y;
+    if (o >= V || k >= K) return;
+    int in = table[(int64_t)k * ld + o];
+    if (in < 0) return;
+    int64_t r = rank[(int64_t)k * V + o];
+    pairs[2 * r] = in;
+    pairs[2 * r + 1] = (int32_t)o;
+}
+__global__ void k_rule_offsets(const int32_t *__restrict__ rank, const int32_t *__restrict__ total, int64_t V, int K,
+                               int32_t *__restrict__ offs) {
+    int k = threadIdx.x;
+    if (k < K) offs[k] = rank[(int64_t)k * V];
+    if (k == K) offs[K] = *total;
+}
+
+// ------------------------------------------------------------------------------------------------ Metadata ops
+int ensure_subm(mopa_scn_metadata *m, int level, cudaStream_t s) {
+    Level &L = m->levels[level];
+    if (L.nbr) return 0;
+    L.nbr_ld = round_up(L.V > 0 ? L.V : 1, 32);
+    MOPA_TRY(meta_alloc(m, (void **)&L.nbr, (size_t)27 * L.nbr_ld * 4, s));
+    if (L.V > 0) {
+        dim3 grid((unsigned)ceil_div(L.V, 256), 27);
+        k_subm_table<<<grid, 256, 0, s>>>(L.keys, L.V, (int)L.spatial, L.tab_keys, L.tab_vals, L.cap - 1, L.nbr, L.nbr_ld);
+        MOPA_LAUNCHED();
+    }
+    return 0;
+}
+
+static int read_back(mopa_scn_metadata *m, const int32_t *dev, int n_ints, cudaStream_t s) {
+    MOPA_CUDA(cudaMemcpyAsync(m->pinned, dev, (size_t)n_ints * 4, cudaMemcpyDeviceToHost, s));
+    MOPA_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int ensure_down(mopa_scn_metadata *m, int level, cudaStream_t s) {
+    if (m->levels[level].has_down) return 0;
+    MOPA_CHECK((int)m->levels.size() == level + 1, "strided levels must be created in order");
+    MOPA_CHECK(m->levels[level].spatial % 2 == 0, "input spatial size must be even for a size-2 stride-2 convolution");
+    m->levels.emplace_back();
+    Level &L = m->levels[level];
+    Level &N = m->levels[level + 1];
+    N.spatial = L.spatial / 2;
+    const int64_t Vf = L.V;
+    N.cap = table_capacity(Vf);
+    MOPA_TRY(meta_alloc(m, (void **)&N.tab_keys, (size_t)N.cap * 8, s));
+    MOPA_TRY(meta_alloc(m, (void **)&N.tab_vals, (size_t)N.cap * 4, s));
+    MOPA_TRY(meta_alloc(m, (void **)&N.keys, (size_t)Vf * 8, s));
+    MOPA_TRY(meta_alloc(m, (void **)&L.parent, (size_t)Vf * 4, s));
+    MOPA_TRY(meta_alloc(m, (void **)&L.kidx, (size_t)Vf * 4, s));
+    int32_t *cnt;
+    MOPA_TRY(tmp_alloc((void **)&cnt, 8, s));
+    MOPA_TRY(unique_first(1, nullptr, 0, 0, L.keys, Vf, N.tab_keys, N.tab_vals, N.cap, N.keys, L.parent, L.kidx, nullptr,
+                          cnt, cnt + 1, s));
+    MOPA_TRY(read_back(m, cnt, 1, s));
+    MOPA_CUDA(cudaFreeAsync(cnt, s));
+    N.V = m->pinned[0];
+    L.child_ld = round_up(N.V > 0 ? N.V : 1, 32);
+    MOPA_TRY(meta_alloc(m, (void **)&L.child, (size_t)8 * L.child_ld * 4, s));
+    MOPA_CUDA(cudaMemsetAsync(L.child, 0xFF, (size_t)8 * L.child_ld * 4, s));
+    if (Vf > 0) {
+        k_child_scatter<<<(unsigned)ceil_div(Vf, 256), 256, 0, s>>>(L.parent, L.kidx, Vf, L.child, L.child_ld);
+        MOPA_LAUNCHED();
+    }
+    L.has_down = true;
+    return 0;
+}
+
+// compact a (K, ld) table with V columns into pairs on the HOST side buffers (inspection only; synchronises)
+static int rulebook_to_host(mopa_scn_metadata *m, const int32_t *table, int64_t ld, int64_t V, int K,
+                            int64_t *counts_host, int32_t *pairs_host, cudaStream_t s) {
+    for (int k = 0; k < K; ++k) counts_host[k] = 0;
+    if (V == 0) return 0;
+    int64_t n = (int64_t)K * V;
+    int32_t *flags, *rank, *bsum, *offs, *pairs = nullptr;
+    MOPA_TRY(tmp_alloc((void **)&flags, n * 4, s));
+    MOPA_TRY(tmp_alloc((void **)&rank, n * 4, s));
+    MOPA_TRY(tmp_alloc((void **)&bsum, ceil_div(n, 1024) * 4, s));
+    MOPA_TRY(tmp_alloc((void **)&offs, 64 * 4, s));
+    dim3 grid((unsigned)ceil_div(V, 1024), K);
+    k_rule_flags<<<grid, 1024, 0, s>>>(table, ld, V, K, flags);
+    MOPA_LAUNCHED();
+    MOPA_TRY(exclusive_scan(flags, rank, n, bsum, offs + 63, s));
+    k_rule_offsets<<<1, 64, 0, s>>>(rank, offs + 63, V, K, offs);
+    MOPA_LAUNCHED();
+    MOPA_TRY(read_back(m, offs, K + 1, s));
+    int64_t total = m->pinned[K];
+    for (int k = 0; k < K; ++k) counts_host[k] = m->pinned[k + 1] - m->pinned[k];
+    if (pairs_host && total > 0) {
+        MOPA_TRY(tmp_alloc((void **)&pairs, total * 8, s));
+        k_rule_write<<<grid, 1024, 0, s>>>(table, ld, V, K, rank, pairs);
+        MOPA_LAUNCHED();
+        MOPA_CUDA(cudaMemcpyAsync(pairs_host, pairs, total * 8, cudaMemcpyDeviceToHost, s));
+        MOPA_CUDA(cudaStreamSynchronize(s));
+        MOPA_CUDA(cudaFreeAsync(pairs, s));
+    }
+    MOPA_CUDA(cudaFreeAsync(flags, s));
+    MOPA_CUDA(cudaFreeAsync(rank, s));
+    MOPA_CUDA(cudaFreeAsync(bsum, s));
+    MOPA_CUDA(cudaFreeAsync(offs, s));
+    return 0;
+}
+
+}  // namespace mopa
+
+using namespace mopa;
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int mopa_scn_abi_version(void) { return MOPA_SCN_ABI_VERSION; }
+const char *mopa_scn_last_error(void) { return g_last_error.c_str(); }
+int64_t mopa_scn_kernelLaunchCount(void) { return (int64_t)g_launches.load(); }
+
+mopa_scn_metadata *mopa_scn_Metadata_new(int dimension, int device) {
+    if (dimension != 3) {
+        fail(__FILE__, __LINE__, "only dimension 3 is supported (scn_unet.py: DIMENSION = 3)");
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        fail(__FILE__, __LINE__, "cudaSetDevice failed: no usable CUDA device (this library has no CPU path)");
+        return nullptr;
+    }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;  // keep freed blocks cached: per-forward scratch is re-used, not re-mapped
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    auto *m = new mopa_scn_metadata();
+    m->device = device;
+    m->pinned = pin_get();
+    if (!m->pinned) {
+        fail(__FILE__, __LINE__, "cudaHostAlloc failed");
+        delete m;
+        return nullptr;
+    }
+    return m;
+}
+
+void mopa_scn_Metadata_delete(mopa_scn_metadata *m) {
+    if (!m) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(m->device);
+    for (void *p : m->allocs) cudaFreeAsync(p, m->last_stream);
+    cudaSetDevice(prev);
+    pin_put(m->pinned);
+    delete m;
+}
+
+int mopa_scn_InputLayer_setLocations(mopa_scn_metadata *m, int64_t spatial_size, const int64_t *coords, int64_t n,
+                                     int ncols, int coords_on_device, int mode, void *stream, int64_t *n_active_out) {
+    MOPA_CHECK(m != nullptr, "null metadata");
+    MOPA_CHECK(mode == 4, "only InputLayer mode 4 (mean) is implemented (scn_unet.py:26)");
+    MOPA_CHECK(ncols == 3 || ncols == 4, "coords must have 3 or 4 columns");
+    MOPA_CHECK(spatial_size > 0 && spatial_size <= 65536, "spatial_size must be in (0, 65536]");
+    MOPA_CHECK(m->levels.empty(), "setLocations called twice on one Metadata");
+    MOPA_CHECK(n >= 0 && n < (int64_t)1 << 30, "point count out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    m->last_stream = s;
+    MOPA_CUDA(cudaSetDevice(m->device));
+    m->levels.emplace_back();
+    Level &L = m->levels[0];
+    L.spatial = spatial_size;
+    m->n_points = n;
+
+    const int64_t *dcoords = coords;
+    int64_t *staged = nullptr;
+    if (!coords_on_device && n > 0) {
+        MOPA_TRY(tmp_alloc((void **)&staged, (size_t)n * ncols * 8, s));
+        MOPA_CUDA(cudaMemcpyAsync(staged, coords, (size_t)n * ncols * 8, cudaMemcpyHostToDevice, s));
+        dcoords = staged;
+    }
+    L.cap = table_capacity(n);
+    MOPA_TRY(meta_alloc(m, (void **)&L.tab_keys, (size_t)L.cap * 8, s));
+    MOPA_TRY(meta_alloc(m, (void **)&L.tab_vals, (size_t)L.cap * 4, s));
+    MOPA_TRY(meta_alloc(m, (void **)&L.keys, (size_t)n * 8, s));
+    MOPA_TRY(meta_alloc(m, (void **)&m->p2v, (size_t)n * 4, s));
+    MOPA_TRY(meta_alloc(m, (void **)&m->csr_off, (size_t)(n + 1) * 4, s));
+    MOPA_TRY(meta_alloc(m, (void **)&m->csr_rows, (size_t)n * 4, s));
+    int32_t *counts, *cnt, *tmp_rows, *bsum;
+    MOPA_TRY(tmp_alloc((void **)&counts, (size_t)(n + 1) * 4, s));
+    MOPA_TRY(tmp_alloc((void **)&cnt, 8, s));
+    MOPA_TRY(tmp_alloc((void **)&tmp_rows, (size_t)n * 4, s));
+    MOPA_TRY(tmp_alloc((void **)&bsum, (size_t)ceil_div(n + 1, 1024) * 4, s));
+    MOPA_CUDA(cudaMemsetAsync(counts, 0, (size_t)(n + 1) * 4, s));
+    MOPA_CUDA(cudaMemsetAsync(cnt, 0, 8, s));
+    MOPA_TRY(unique_first(0, dcoords, ncols, spatial_size, nullptr, n, L.tab_keys, L.tab_vals, L.cap, L.keys, m->p2v,
+                          nullptr, counts, cnt, cnt + 1, s));
+    if (n > 0) {
+        // CSR offsets over the (n + 1)-long zero-padded count array: off[v] valid for v <= V0, off[V0] = n
+        MOPA_TRY(exclusive_scan(counts, m->csr_off, n + 1, bsum, nullptr, s));
+        MOPA_CUDA(cudaMemsetAsync(counts, 0, (size_t)n * 4, s));  // reuse as per-voxel cursor
+        unsigned g = (unsigned)ceil_div(n, 256);
+        k_csr_fill<<<g, 256, 0, s>>>(m->p2v, m->csr_off, n, counts, tmp_rows);
+        MOPA_LAUNCHED();
+        k_csr_order<<<g, 256, 0, s>>>(m->p2v, m->csr_off, tmp_rows, n, m->csr_rows);
+        MOPA_LAUNCHED();
+    } else {
+        MOPA_CUDA(cudaMemsetAsync(m->csr_off, 0, 4, s));
+    }
+    MOPA_TRY(read_back(m, cnt, 2, s));
+    L.V = m->pinned[0];
+    int err = m->pinned[1];
+    MOPA_CUDA(cudaFreeAsync(counts, s));
+    MOPA_CUDA(cudaFreeAsync(cnt, s));
+    MOPA_CUDA(cudaFreeAsync(tmp_rows, s));
+    MOPA_CUDA(cudaFreeAsync(bsum, s));
+    if (staged) MOPA_CUDA(cudaFreeAsync(staged, s));
+    MOPA_CHECK(err == 0, "InputLayer: coordinates outside [0, spatial_size) or batch index outside [0, 65535)");
+    if (n_active_out) *n_active_out = L.V;
+    return 0;
+}
+
+int mopa_scn_Metadata_prepareSubmanifold(mopa_scn_metadata *m, int64_t spatial_size, int filter_size, void *stream,
+                                         int64_t *n_active_out) {
+    MOPA_CHECK(m != nullptr, "null metadata");
+    MOPA_CHECK(filter_size == 3, "only 3x3x3 submanifold filters are implemented");
+    int l = m->level_of(spatial_size);
+    MOPA_CHECK(l >= 0, "no grid at this spatial size (call InputLayer / Convolution first)");
+    m->last_stream = (cudaStream_t)stream;
+    MOPA_CUDA(cudaSetDevice(m->device));
+    MOPA_TRY(ensure_subm(m, l, (cudaStream_t)stream));
+    if (n_active_out) *n_active_out = m->levels[l].V;
+    return 0;
+}
+
+int mopa_scn_Metadata_prepareConvolution(mopa_scn_metadata *m, int64_t in_spatial_size, int64_t out_spatial_size,
+                                         int filter_size, int filter_stride, void *stream, int64_t *n_active_out) {
+    MOPA_CHECK(m != nullptr, "null metadata");
+    MOPA_CHECK(filter_size == 2 && filter_stride == 2, "only size-2 stride-2 (de)convolutions are implemented");
+    MOPA_CHECK((out_spatial_size - 1) * filter_stride + filter_size == in_spatial_size,
+               "Convolution: (out - 1) * stride + size must equal the input spatial size");
+    int l = m->level_of(in_spatial_size);
+    MOPA_CHECK(l >= 0, "no grid at the input spatial size");
+    m->last_stream = (cudaStream_t)stream;
+    MOPA_CUDA(cudaSetDevice(m->device));
+    MOPA_TRY(ensure_down(m, l, (cudaStream_t)stream));
+    if (n_active_out) *n_active_out = m->levels[l + 1].V;
+    return 0;
+}
+
+int64_t mopa_scn_Metadata_getNActive(mopa_scn_metadata *m, int64_t spatial_size) {
+    if (!m) return -1;
+    int l = m->level_of(spatial_size);
+    return l < 0 ? -1 : m->levels[l].V;
+}
+int64_t mopa_scn_Metadata_getNPoints(mopa_scn_metadata *m) { return m ? m->n_points : -1; }
+
+int64_t mopa_scn_Metadata_getSubmanifoldRuleCount(mopa_scn_metadata *m, int64_t spatial_size) {
+    // upper bound usable for workspace sizing without a device round trip: every site has at most 27 rules
+    if (!m) return -1;
+    int l = m->level_of(spatial_size);
+    return l < 0 ? -1 : 27 * m->levels[l].V;
+}
+
+int mopa_scn_Metadata_getSpatialLocations(mopa_scn_metadata *m, int64_t spatial_size, int64_t *coords_host) {
+    MOPA_CHECK(m != nullptr, "null metadata");
+    int l = m->level_of(spatial_size);
+    MOPA_CHECK(l >= 0, "no grid at this spatial size");
+    const Level &L = m->levels[l];
+    std::vector<uint64_t> keys((size_t)L.V);
+    MOPA_CUDA(cudaSetDevice(m->device));
+    MOPA_CUDA(cudaStreamSynchronize(m->last_stream));
+    if (L.V) MOPA_CUDA(cudaMemcpy(keys.data(), L.keys, (size_t)L.V * 8, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < L.V; ++i) {
+        int x, y, z, b;
+        unpack_key(keys[(size_t)i], x, y, z, b);
+        coords_host[4 * i] = x; coords_host[4 * i + 1] = y; coords_host[4 * i + 2] = z; coords_host[4 * i + 3] = b;
+    }
+    return 0;
+}
+
+int mopa_scn_Metadata_getPointToVoxel(mopa_scn_metadata *m, int32_t *p2v_host) {
+    MOPA_CHECK(m != nullptr && !m->levels.empty(), "metadata has no input layer");
+    MOPA_CUDA(cudaSetDevice(m->device));
+    MOPA_CUDA(cudaStreamSynchronize(m->last_stream));
+    if (m->n_points) MOPA_CUDA(cudaMemcpy(p2v_host, m->p2v, (size_t)m->n_points * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int mopa_scn_Metadata_getInputRules(mopa_scn_metadata *m, int32_t *off_host, int32_t *rows_host) {
+    MOPA_CHECK(m != nullptr && !m->levels.empty(), "metadata has no input layer");
+    MOPA_CUDA(cudaSetDevice(m->device));
+    MOPA_CUDA(cudaStreamSynchronize(m->last_stream));
+    MOPA_CUDA(cudaMemcpy(off_host, m->csr_off, (size_t)(m->levels[0].V + 1) * 4, cudaMemcpyDeviceToHost));
+    if (m->n_points) MOPA_CUDA(cudaMemcpy(rows_host, m->csr_rows, (size_t)m->n_points * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int mopa_scn_Metadata_getSubmanifoldRuleBook(mopa_scn_metadata *m, int64_t spatial_size, int64_t *counts_host,
+                                             int32_t *pairs_host) {
+    MOPA_CHECK(m != nullptr, "null metadata");
+    int l = m->level_of(spatial_size);
+    MOPA_CHECK(l >= 0, "no grid at this spatial size");
+    MOPA_CUDA(cudaSetDevice(m->device));
+    MOPA_TRY(ensure_subm(m, l, m->last_stream));
+    const Level &L = m->levels[l];
+    return rulebook_to_host(m, L.nbr, L.nbr_ld, L.V, 27, counts_host, pairs_host, m->last_stream);
+}
+
+int mopa_scn_Metadata_getConvolutionRuleBook(mopa_scn_metadata *m, int64_t in_spatial_size, int64_t *counts_host,
+                                             int32_t *pairs_host) {
+    MOPA_CHECK(m != nullptr, "null metadata");
+    int l = m->level_of(in_spatial_size);
+    MOPA_CHECK(l >= 0, "no grid at this spatial size");
+    MOPA_CUDA(cudaSetDevice(m->device));
+    MOPA_TRY(ensure_down(m, l, m->last_stream));
+    const Level &L = m->levels[l];
+    return rulebook_to_host(m, L.child, L.child_ld, m->levels[l + 1].V, 8, counts_host, pairs_host, m->last_stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,63 @@
+// Metadata: per-forward GPU hash grids, neighbour tables and rulebooks (replaces [UPSTREAM] Metadata<3>).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace mopa {
+
+struct Level {
+    int64_t spatial = 0;
+    int64_t V = 0;                 // active sites
+    uint64_t *keys = nullptr;      // [V] packed site keys, id order
+    uint64_t *tab_keys = nullptr;  // open-addressing table: key -> id
+    int32_t *tab_vals = nullptr;
+    uint32_t cap = 0;  // power of two
+    // 3x3x3 submanifold neighbour table: nbr[k * nbr_ld + o] = id at coord(o) + delta_k, or -1
+    int32_t *nbr = nullptr;
+    int64_t nbr_ld = 0;
+    // stride-2 link to the next (coarser) level
+    bool has_down = false;
+    int32_t *parent = nullptr;  // [V] coarse id
+    int32_t *kidx = nullptr;    // [V] (x&1)*4 + (y&1)*2 + (z&1)
+    int32_t *child = nullptr;   // [8 * child_ld] fine id or -1, indexed by coarse id
+    int64_t child_ld = 0;
+};
+
+}  // namespace mopa
+
+struct mopa_scn_metadata {
+    int device = 0;
+    std::vector<mopa::Level> levels;  // levels[0] = InputLayer's spatial size, levels[l].spatial = spatial >> l
+    int64_t n_points = 0;
+    int32_t *p2v = nullptr;       // [n_points]
+    int32_t *csr_off = nullptr;   // [V0 + 1]
+    int32_t *csr_rows = nullptr;  // [n_points] ascending inside a voxel
+    std::vector<void *> allocs;
+    cudaStream_t last_stream = nullptr;
+    int32_t *pinned = nullptr;  // small host staging block for counts
+
+    int level_of(int64_t spatial) const {
+        for (size_t l = 0; l < levels.size(); ++l)
+            if (levels[l].spatial == spatial) return (int)l;
+        return -1;
+    }
+};
+
+namespace mopa {
+// how a conv kernel finds the input row of (offset k, output row o)
+struct Gather {
+    // table mode: table[k * ld + o]; select mode (table == nullptr): kidx[o] == k ? parent[o] : -1
+    const int32_t *table = nullptr;
+    int64_t ld = 0;
+    const int32_t *parent = nullptr;
+    const int32_t *kidx = nullptr;
+    int volume = 0;     // 27 or 8
+    int64_t n_out = 0;  // output rows
+    int64_t n_in = 0;   // input rows (for bounds/debug)
+};
+
+int meta_alloc(mopa_scn_metadata *m, void **p, size_t bytes, cudaStream_t s);
+int ensure_subm(mopa_scn_metadata *m, int level, cudaStream_t s);
+int ensure_down(mopa_scn_metadata *m, int level, cudaStream_t s);
+}  // namespace mopa
