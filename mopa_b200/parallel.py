@@ -1,0 +1,55 @@
+"""Scan-sharded data parallelism for the 3D branch (new: the reference is single-process).
+
+One process per GPU; every rank holds a full UNetSCN replica and its own scans (a scan is never split); BatchNorm
+statistics stay per rank, as in the reference's single-GPU batch of 8. The only exchange is one gradient all-reduce
+(mean) per optimizer step over NCCL/NVLink: all gradients live in ONE flat fp32 bucket (~10.8 MB for UNetSCN) that
+autograd accumulates into directly, so the collective needs no packing copies and MoPA's two backward() calls per step
+(train_xmuda_mopa.py:417-418,578-579) reduce once.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_scans(n_scans, rank, world_size):
+    """Indices of the scans rank `rank` owns: contiguous, sizes differ by at most one, every scan owned exactly once."""
+    base, extra = divmod(n_scans, world_size)
+    start = rank * base + min(rank, extra)
+    return list(range(start, start + base + (1 if rank < extra else 0)))
+
+
+class FlatGradBucket:
+    """Points every parameter's .grad at a slice of one flat buffer; all_reduce() averages it across ranks in place."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev, dtype = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=dtype, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce(self, async_op=False):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return None
+        if dist.get_backend() == "nccl":
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, async_op=async_op)
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)  # gloo has no AVG
+        if async_op:
+            raise NotImplementedError("async all-reduce is only wired for nccl")
+        self.flat.div_(dist.get_world_size())
+        return work
+
+
+def broadcast_parameters(module, src=0):
+    """Make every rank start from rank `src`'s parameters and buffers."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src)

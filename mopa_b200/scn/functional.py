@@ -13,6 +13,10 @@ from .. import _lib
 
 _cfg = {"precision": _lib.PREC_TF32}
 
+# bench.py's roofline leg: when this is a list, every conv forward kernel is bracketed by CUDA events on the
+# launching stream and (kind, events, shape info) is appended. None (default) = no instrumentation at all.
+profile_log = None
+
 
 def set_precision(name):
     """'tf32' (default: one TF32 MMA per product) or 'fp32' (3xTF32 split operands: fp32-equivalent, ~3x the MMA work)."""
@@ -122,6 +126,12 @@ class Metadata:
         _lib.check(fn(self._h, int(spatial_size), counts.data_ptr(), pairs.data_ptr()))
         return list(torch.split(pairs, counts.tolist()))
 
+    def submanifold_rule_counts(self, spatial_size):
+        """rules per offset (27 ints) of the 3x3x3 rulebook at this level"""
+        counts = torch.zeros(27, dtype=torch.int64)
+        _lib.check(self._lib.mopa_scn_Metadata_getSubmanifoldRuleBook(self._h, int(spatial_size), counts.data_ptr(), None))
+        return counts.tolist()
+
     def submanifold_rulebook(self, spatial_size):
         """list over the 27 offsets of (R_k, 2) int32 [in, out], ascending out row"""
         return self._rulebook(self._lib.mopa_scn_Metadata_getSubmanifoldRuleBook, spatial_size, 27)
@@ -176,13 +186,13 @@ class InputLayerFunction(Function):
         out = torch.empty(n_active, feats.shape[1], dtype=torch.float32, device=feats.device)
         _lib.check(metadata._lib.mopa_scn_InputLayer_updateOutput(metadata._h, feats.data_ptr(), ld, feats.shape[1],
                                                                   out.data_ptr(), max(feats.shape[1], 1), _stream()))
-        ctx.metadata = metadata
+        ctx.meta = metadata
         ctx.n_rows = feats.shape[0]
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        m = ctx.metadata
+        m = ctx.meta
         d_out, ld = _rows(d_out)
         planes = d_out.shape[1]
         d_in = torch.zeros(ctx.n_rows, planes, dtype=torch.float32, device=d_out.device)
@@ -200,13 +210,13 @@ class OutputLayerFunction(Function):
         out = torch.empty(metadata.n_points, planes, dtype=torch.float32, device=feats.device)
         _lib.check(metadata._lib.mopa_scn_OutputLayer_updateOutput(metadata._h, feats.data_ptr(), ld, planes, out.data_ptr(),
                                                                    planes, _stream()))
-        ctx.metadata = metadata
+        ctx.meta = metadata
         ctx.n_active = feats.shape[0]
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        m = ctx.metadata
+        m = ctx.meta
         d_out, ld = _rows(d_out)
         planes = d_out.shape[1]
         d_in = torch.empty(ctx.n_active, planes, dtype=torch.float32, device=d_out.device)
@@ -231,6 +241,9 @@ class _ConvFunction(Function):
         packed = _pack(w, volume, n_in, n_out, 0, 0)
         prec = _cfg["precision"]
         s = _stream()
+        if profile_log is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         if kind == "subm":
             st = L.mopa_scn_SubmanifoldConvolution_updateOutput(metadata._h, sizes[0], filter_size, feats.data_ptr(), ld_in,
                                                                 out.data_ptr(), n_out, w.data_ptr(), _ptr(packed), n_in,
@@ -244,14 +257,18 @@ class _ConvFunction(Function):
                                                        feats.data_ptr(), ld_in, out.data_ptr(), n_out, w.data_ptr(),
                                                        _ptr(packed), n_in, n_out, prec, s)
         _lib.check(st)
+        if profile_log is not None:
+            ev1.record()
+            profile_log.append({"kind": kind, "ev": (ev0, ev1), "metadata": metadata, "size": sizes[0], "volume": volume,
+                                "n_in": n_in, "n_out": n_out, "rows_in": feats.shape[0], "rows_out": n_out_rows})
         ctx.save_for_backward(feats, w)
-        ctx.metadata, ctx.kind, ctx.sizes, ctx.fs = metadata, kind, sizes, (filter_size, stride)
+        ctx.meta, ctx.kind, ctx.sizes, ctx.fs = metadata, kind, sizes, (filter_size, stride)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         feats, w = ctx.saved_tensors
-        m, kind, sizes = ctx.metadata, ctx.kind, ctx.sizes
+        m, kind, sizes = ctx.meta, ctx.kind, ctx.sizes
         filter_size, stride = ctx.fs
         L = m._lib
         d_out, ld_dout = _rows(d_out)

@@ -122,3 +122,20 @@ def test_unet_is_translation_invariant_for_multiples_of_64():
     shifted[:, :3] += np.array([64, 128, 192]) - (coords[:, :3].min(0) // 64) * 64
     b = so.OracleUNetSCN(st).forward(shifted, feats)
     assert torch.equal(a, b)
+
+
+def test_golden_fixture_reproduces_on_cpu():
+    """The committed fixture is what the oracle computes today (guards against silent oracle drift)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet_small.npz"))
+    st = so.make_unet_state(seed=int(z["state_seed"]))
+    net = so.OracleUNetSCN(st, dtype=torch.float64)
+    out = net.forward(z["coords"], z["feats"])
+    assert np.array_equal(net.geo.p2v, z["p2v"])
+    assert [net.geo.n_active(l) for l in range(7)] == z["n_active"].tolist()
+    assert np.allclose(out.detach().numpy(), z["out"], rtol=0, atol=1e-9)
+    out.backward(torch.from_numpy(z["grad_out"]).double())
+    assert np.allclose(net.params["sparseModel.1.weight"].grad.numpy(), z["grad_w1"], rtol=1e-9, atol=1e-9)
+    # float32 oracle within the fp32 bar of the GPU tests
+    o32 = so.OracleUNetSCN(st).forward(z["coords"], z["feats"])
+    assert float((o32.double() - out).abs().max() / out.abs().max()) < 5e-4
