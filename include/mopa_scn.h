@@ -152,6 +152,32 @@ int mopa_scn_BatchNormalization_backward(const float *in, int64_t ld_in, float *
                                          float *d_weight, float *d_bias, float leakiness, int train, int64_t n_active,
                                          int planes, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- whole-network executor ------------------------------------------------------------------------------------
+ * Replaces the Python-level module loop of scn.Sequential.forward (mopa/models/scn_unet.py:32-34 -> [UPSTREAM]
+ * sequential.py) for a compiled InputLayer ... OutputLayer chain: one call enqueues every kernel of the forward (or
+ * backward) pass. ops: n_ops rows of 12 int32 {type (1 subm, 2 conv, 3 deconv, 4 batchnorm), in_buf, out_buf, 0,
+ * level_in, level_out, n_in, n_out, param_index, leakiness, eps, momentum (float bits)}; bufs: n_bufs rows of 4 int32
+ * {level, channels, parent_buf (-1 = owns storage; else a column slice of the joined parent), column offset}.
+ * params / param_grads: arrays of DEVICE pointers indexed by param_index: conv -> {weight}; batchnorm -> {weight, bias,
+ * running_mean, running_var}. Arenas are caller-allocated device scratch of the sizes _prepare reports. */
+typedef struct mopa_scn_program mopa_scn_program;
+mopa_scn_program *mopa_scn_Program_new(const int32_t *ops, int n_ops, const int32_t *bufs, int n_bufs, int in_planes,
+                                       int in_buf, int out_buf, int64_t spatial_size, int n_levels, int device);
+void mopa_scn_Program_delete(mopa_scn_program *p);
+/* voxelise `coords` (as InputLayer_setLocations) and build every grid / table the program needs on a dedicated
+ * high-priority stream; `stream` is made to wait for it. n_active_out[n_levels]; sizes_out = {activation arena bytes,
+ * gradient arena bytes, scratch bytes}. */
+int mopa_scn_Program_prepare(mopa_scn_program *p, mopa_scn_metadata *m, const int64_t *coords, int64_t n, int ncols,
+                             int coords_on_device, int precision, void *stream, int64_t *n_active_out,
+                             uint64_t *sizes_out);
+int mopa_scn_Program_forward(mopa_scn_program *p, mopa_scn_metadata *m, const float *feats, int64_t ld_feats,
+                             const void *const *params, int train, int precision, void *act_arena, void *scratch,
+                             float *out, int64_t ld_out, void *stream);
+int mopa_scn_Program_backward(mopa_scn_program *p, mopa_scn_metadata *m, const void *const *params,
+                              void *const *param_grads, int train, int precision, const void *act_arena,
+                              void *grad_arena, void *scratch, const float *d_out, int64_t ld_dout, float *d_feats,
+                              int64_t ld_dfeats, void *stream);
+
 /* ---- instrumentation: number of kernels this library has launched in this process (bench.py `gpu_launches`) --- */
 int64_t mopa_scn_kernelLaunchCount(void);
 

@@ -51,6 +51,11 @@ PROTOTYPES = {
     "mopa_scn_bnWorkspaceBytes": (_sz, [_int]),
     "mopa_scn_BatchNormalization_updateOutput": (_int, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _f, _f, _int, _f, _i64, _int, _p, _sz, _p]),
     "mopa_scn_BatchNormalization_backward": (_int, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _f, _int, _i64, _int, _p, _sz, _p]),
+    "mopa_scn_Program_new": (_p, [_p, _int, _p, _int, _int, _int, _int, _i64, _int, _int]),
+    "mopa_scn_Program_delete": (None, [_p]),
+    "mopa_scn_Program_prepare": (_int, [_p, _p, _p, _i64, _int, _int, _int, _p, _p, _p]),
+    "mopa_scn_Program_forward": (_int, [_p, _p, _p, _i64, _p, _int, _int, _p, _p, _p, _i64, _p]),
+    "mopa_scn_Program_backward": (_int, [_p, _p, _p, _p, _int, _int, _p, _p, _p, _p, _i64, _p, _i64, _p]),
     "mopa_scn_kernelLaunchCount": (_i64, []),
 }
 

@@ -58,27 +58,38 @@ __global__ void __launch_bounds__(256) k_bn_stats(const float *__restrict__ x, i
             ref[e] = x[c0 + e];
         }
     }
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; r < n; r += (int64_t)gridDim.x * blockDim.y) {
-        float v[VEC];
-        Vec<VEC>::get(x + r * ld_x + c0, v);
-        if (BWD) {
-            float d[VEC];
-            Vec<VEC>::get(dout + r * ld_dout + c0, d);
+    auto accumulate = [&](const float (&v)[VEC], const float (&d)[VEC]) {
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
+        for (int e = 0; e < VEC; ++e) {
+            if (BWD) {
                 const float y = fmaf(v[e], sc[e], sh[e]);
                 const float dm = y > 0.f ? d[e] : d[e] * leakiness;
                 s1[e] += dm;
                 s2[e] = fmaf(v[e] - ref[e], dm, s2[e]);
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
+            } else {
                 const float dv = v[e] - ref[e];
                 s1[e] += dv;
                 s2[e] = fmaf(dv, dv, s2[e]);
             }
         }
+    };
+    const int64_t stride = (int64_t)gridDim.x * blockDim.y;
+    int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    for (; r + 3 * stride < n; r += 4 * stride) {  // four independent rows in flight per thread
+        float v[4][VEC], d[4][VEC];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            Vec<VEC>::get(x + (r + q * stride) * ld_x + c0, v[q]);
+            if (BWD) Vec<VEC>::get(dout + (r + q * stride) * ld_dout + c0, d[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) accumulate(v[q], d[q]);
+    }
+    for (; r < n; r += stride) {
+        float v[VEC], d[VEC];
+        Vec<VEC>::get(x + r * ld_x + c0, v);
+        if (BWD) Vec<VEC>::get(dout + r * ld_dout + c0, d);
+        accumulate(v, d);
     }
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
@@ -106,11 +117,30 @@ __global__ void __launch_bounds__(256) k_bn_stats(const float *__restrict__ x, i
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    // column sums of the partials: J threads per column, 4 independent accumulators each, then a shared-memory combine
+    __shared__ double sfin[512];
+    const int cols = 2 * planes;
+    int J = nthr / cols;
+    J = J < 1 ? 1 : (J > 8 ? 8 : J);
+    for (int e = tid; e < J * cols; e += nthr) {
+        const int j = e / cols, col = e - j * cols;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int blk = j;
+        for (; blk + 3 * J < (int)gridDim.x; blk += 4 * J) {
+            a0 += (double)__ldcg(partial + (int64_t)blk * cols + col);
+            a1 += (double)__ldcg(partial + (int64_t)(blk + J) * cols + col);
+            a2 += (double)__ldcg(partial + (int64_t)(blk + 2 * J) * cols + col);
+            a3 += (double)__ldcg(partial + (int64_t)(blk + 3 * J) * cols + col);
+        }
+        for (; blk < (int)gridDim.x; blk += J) a0 += (double)__ldcg(partial + (int64_t)blk * cols + col);
+        sfin[e] = (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
     for (int c = tid; c < planes; c += nthr) {
         double a = 0.0, b = 0.0;
-        for (int blk = 0; blk < (int)gridDim.x; ++blk) {
-            a += (double)__ldcg(partial + (int64_t)blk * 2 * planes + c);
-            b += (double)__ldcg(partial + (int64_t)blk * 2 * planes + planes + c);
+        for (int j = 0; j < J; ++j) {
+            a += sfin[j * cols + c];
+            b += sfin[j * cols + planes + c];
         }
         const double dn = (double)n;
         if (!BWD) {
@@ -171,7 +201,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float *__restrict__ 
                                                       float *__restrict__ din, int64_t ld_din, int64_t n, int planes,
                                                       const float *__restrict__ mean, const float *__restrict__ invstd,
                                                       const float *__restrict__ weight, const float *__restrict__ bias,
-                                                      const float *__restrict__ ws, float leakiness) {
+                                                      const float *__restrict__ ws, float leakiness, int accumulate) {
     const int c0 = threadIdx.x * VEC;
     float sc[VEC], sh[VEC], mu[VEC], gm[VEC], kk[VEC];
 #pragma unroll
@@ -191,6 +221,12 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float *__restrict__ 
             const float y = fmaf(v[e], sc[e], sh[e]);
             const float dm = y > 0.f ? d[e] : d[e] * leakiness;
             v[e] = (dm - gm[e] - (v[e] - mu[e]) * kk[e]) * sc[e];
+        }
+        if (accumulate) {
+            float old[VEC];
+            Vec<VEC>::get(din + r * ld_din + c0, old);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v[e] = __fadd_rn(v[e], old[e]);  // no FMA contraction: same bits as a separate add
         }
         Vec<VEC>::put(din + r * ld_din + c0, v);
     }
@@ -278,26 +314,17 @@ __global__ void __launch_bounds__(256) k_unpool_bwd(float *__restrict__ din, int
     Vec<VEC>::put(din + v * ld_din + c, acc);
 }
 
-}  // namespace mopa
+size_t bn_workspace_bytes(int planes) { return bn_ws_floats(planes) * 4; }
 
-using namespace mopa;
-
-extern "C" {
-
-size_t mopa_scn_bnWorkspaceBytes(int planes) { return bn_ws_floats(planes) * 4; }
-
-int mopa_scn_BatchNormalization_updateOutput(const float *in, int64_t ld_in, float *out, int64_t ld_out,
-                                             float *save_mean, float *save_invstd, float *running_mean,
-                                             float *running_var, const float *weight, const float *bias, float eps,
-                                             float momentum, int train, float leakiness, int64_t n_active, int planes,
-                                             void *workspace, size_t workspace_bytes, void *stream) {
-    MOPA_CHECK(planes > 0 && planes <= 1024, "BatchNormalization: planes out of range");
-    MOPA_CHECK(workspace && workspace_bytes >= mopa_scn_bnWorkspaceBytes(planes), "BatchNormalization: workspace too small");
+int bn_forward(const float *in, int64_t ld_in, float *out, int64_t ld_out, float *save_mean, float *save_invstd,
+               float *running_mean, float *running_var, const float *weight, const float *bias, float eps, float momentum,
+               int train, float leakiness, int64_t n_active, int planes, void *workspace, cudaStream_t s) {
+    MOPA_CHECK(planes > 0 && planes <= 256, "BatchNormalization: planes must be in [1, 256]");
     MOPA_CHECK(weight && bias, "BatchNormalization: affine parameters are required");
-    cudaStream_t s = (cudaStream_t)stream;
     if (n_active == 0) return 0;
     const bool vec_ok = al16(in) && al16(out) && ld_in % 4 == 0 && ld_out % 4 == 0;
     BnShape sh = bn_shape(n_active, planes, vec_ok);
+    MOPA_CHECK(sh.block.x * sh.block.y <= 256, "BatchNormalization: unaligned features with more than 256 planes");
     float *ws = reinterpret_cast<float *>(workspace);
     if (train) {
         if (sh.vec == 4)
@@ -325,14 +352,11 @@ int mopa_scn_BatchNormalization_updateOutput(const float *in, int64_t ld_in, flo
     return 0;
 }
 
-int mopa_scn_BatchNormalization_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din,
-                                         const float *d_out, int64_t ld_dout, const float *save_mean,
-                                         const float *save_invstd, const float *weight, const float *bias,
-                                         float *d_weight, float *d_bias, float leakiness, int train, int64_t n_active,
-                                         int planes, void *workspace, size_t workspace_bytes, void *stream) {
-    MOPA_CHECK(planes > 0 && planes <= 1024, "BatchNormalization: planes out of range");
-    MOPA_CHECK(workspace && workspace_bytes >= mopa_scn_bnWorkspaceBytes(planes), "BatchNormalization: workspace too small");
-    cudaStream_t s = (cudaStream_t)stream;
+int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, const float *d_out, int64_t ld_dout,
+                const float *save_mean, const float *save_invstd, const float *weight, const float *bias, float *d_weight,
+                float *d_bias, float leakiness, int train, int64_t n_active, int planes, void *workspace, int accumulate,
+                cudaStream_t s) {
+    MOPA_CHECK(planes > 0 && planes <= 256, "BatchNormalization: planes must be in [1, 256]");
     if (n_active == 0) {
         if (d_weight) MOPA_CUDA(cudaMemsetAsync(d_weight, 0, (size_t)planes * 4, s));
         if (d_bias) MOPA_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)planes * 4, s));
@@ -340,6 +364,7 @@ int mopa_scn_BatchNormalization_backward(const float *in, int64_t ld_in, float *
     }
     const bool vec_ok = al16(in) && al16(d_in) && al16(d_out) && ld_in % 4 == 0 && ld_din % 4 == 0 && ld_dout % 4 == 0;
     BnShape sh = bn_shape(n_active, planes, vec_ok);
+    MOPA_CHECK(sh.block.x * sh.block.y <= 256, "BatchNormalization: unaligned features with more than 256 planes");
     float *ws = reinterpret_cast<float *>(workspace);
     if (sh.vec == 4)
         k_bn_stats<4, true><<<sh.grid, sh.block, sh.smem, s>>>(in, ld_in, d_out, ld_dout, n_active, planes, ws, save_mean,
@@ -353,13 +378,41 @@ int mopa_scn_BatchNormalization_backward(const float *in, int64_t ld_in, float *
     if (d_in) {
         if (sh.vec == 4)
             k_bn_bwd_apply<4><<<sh.grid, sh.block, 0, s>>>(in, ld_in, d_out, ld_dout, d_in, ld_din, n_active, planes,
-                                                           save_mean, save_invstd, weight, bias, ws, leakiness);
+                                                           save_mean, save_invstd, weight, bias, ws, leakiness, accumulate);
         else
             k_bn_bwd_apply<1><<<sh.grid, sh.block, 0, s>>>(in, ld_in, d_out, ld_dout, d_in, ld_din, n_active, planes,
-                                                           save_mean, save_invstd, weight, bias, ws, leakiness);
+                                                           save_mean, save_invstd, weight, bias, ws, leakiness, accumulate);
         MOPA_LAUNCHED();
     }
     return 0;
+}
+
+}  // namespace mopa
+
+using namespace mopa;
+
+extern "C" {
+
+size_t mopa_scn_bnWorkspaceBytes(int planes) { return bn_workspace_bytes(planes); }
+
+int mopa_scn_BatchNormalization_updateOutput(const float *in, int64_t ld_in, float *out, int64_t ld_out,
+                                             float *save_mean, float *save_invstd, float *running_mean,
+                                             float *running_var, const float *weight, const float *bias, float eps,
+                                             float momentum, int train, float leakiness, int64_t n_active, int planes,
+                                             void *workspace, size_t workspace_bytes, void *stream) {
+    MOPA_CHECK(workspace && workspace_bytes >= bn_workspace_bytes(planes), "BatchNormalization: workspace too small");
+    return bn_forward(in, ld_in, out, ld_out, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum,
+                      train, leakiness, n_active, planes, workspace, (cudaStream_t)stream);
+}
+
+int mopa_scn_BatchNormalization_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din,
+                                         const float *d_out, int64_t ld_dout, const float *save_mean,
+                                         const float *save_invstd, const float *weight, const float *bias,
+                                         float *d_weight, float *d_bias, float leakiness, int train, int64_t n_active,
+                                         int planes, void *workspace, size_t workspace_bytes, void *stream) {
+    MOPA_CHECK(workspace && workspace_bytes >= bn_workspace_bytes(planes), "BatchNormalization: workspace too small");
+    return bn_backward(in, ld_in, d_in, ld_din, d_out, ld_dout, save_mean, save_invstd, weight, bias, d_weight, d_bias,
+                       leakiness, train, n_active, planes, workspace, 0, (cudaStream_t)stream);
 }
 
 static int io_check(mopa_scn_metadata *m, int planes) {

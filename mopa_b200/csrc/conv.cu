@@ -51,38 +51,36 @@ __device__ __forceinline__ int gather_lookup(const Gather &g, int k, int64_t row
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
-// K-chunk of the contraction axis staged per pipeline step (multiple of 16 dividing c_in, stage <= 56 KB).
-__host__ __device__ inline int choose_kc(int c_in, int c_out, int split) {
-    if (split) return 16;
-    int best = 16;
-    for (int kc = 16; kc <= c_in; kc += 16)
-        if (c_in % kc == 0 && (int64_t)kc * c_out * 4 <= 56 * 1024) best = kc;
-    return best;
-}
-
-// channel of (k-step s, fragment slot q) inside a K-chunk, and output channel of (n-tile p, fragment column c):
-// the permutations that let one float4 feed two k-steps and one thread own 4 contiguous output channels.
+// The contraction axis is cut into chunks of 32 channels (the last one 16 when c_in % 32 == 16); one (offset, chunk) pair
+// is one pipeline step whose weights (chunk x c_out floats, fragment order) are one contiguous block: a single TMA
+// bulk copy. Channel of (k-step s, fragment slot q) inside a chunk, and output channel of (n-tile p, column c): the
+// permutations that let one float4 feed two k-steps and one thread own 4 contiguous output channels.
+constexpr int kChunk = 32;
 __host__ __device__ inline int frag_k_channel(int s, int q) { return 16 * (s >> 1) + 4 * (q & 3) + 2 * (s & 1) + (q >> 2); }
 __host__ __device__ inline int frag_n_channel(int p, int c) { return 16 * (p >> 1) + 4 * (c >> 1) + 2 * (p & 1) + (c & 1); }
 
 // packed[k][chunk][half][kstep][npair][lane][4]; half = hi / lo tf32 parts when split
 __global__ void __launch_bounds__(256) k_pack_weights(const float *__restrict__ w, int volume, int n_in0, int n_out0,
-                                                      int transpose, int flip, int split, int kc,
-                                                      float *__restrict__ packed, int64_t total) {
+                                                      int transpose, int flip, int split, float *__restrict__ packed,
+                                                      int64_t total) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int c_in = transpose ? n_out0 : n_in0, c_out = transpose ? n_in0 : n_out0;
-    const int npair = c_out / 16, nsteps = kc / 8, halves = split ? 2 : 1;
-    int64_t r = idx;
+    const int npair = c_out / 16, halves = split ? 2 : 1;
+    const int64_t per_k = (int64_t)c_in * c_out * halves;
+    const int k = (int)(idx / per_k);
+    int64_t r = idx - (int64_t)k * per_k;
+    const int chunk = (int)(r / ((int64_t)kChunk * c_out * halves));
+    r -= (int64_t)chunk * kChunk * c_out * halves;
+    const int kc = min(kChunk, c_in - chunk * kChunk);
+    const int half = (int)(r / ((int64_t)kc * c_out));
+    r -= (int64_t)half * kc * c_out;
     const int e4 = r & 3; r >>= 2;
     const int lane = r & 31; r >>= 5;
-    const int u = r % npair; r /= npair;
-    const int s = r % nsteps; r /= nsteps;
-    const int half = r % halves; r /= halves;
-    const int chunk = r % (c_in / kc); r /= (c_in / kc);
-    const int k = (int)r;
+    const int u = (int)(r % npair);
+    const int s = (int)(r / npair);
     const int g = lane >> 2, t = lane & 3;
-    const int ci = chunk * kc + frag_k_channel(s, t + 4 * (e4 & 1));
+    const int ci = chunk * kChunk + frag_k_channel(s, t + 4 * (e4 & 1));
     const int co = frag_n_channel(2 * u + (e4 >> 1), g);
     const int ks = flip ? volume - 1 - k : k;
     float v = transpose ? w[((int64_t)ks * n_in0 + co) * n_out0 + ci] : w[((int64_t)ks * n_in0 + ci) * n_out0 + co];
@@ -90,23 +88,65 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float *__restrict__ 
     packed[idx] = half == 0 ? hi : __uint_as_float(to_tf32(v - hi));
 }
 
+// ------------------------------------------------------------------------------------------------ mbarrier / TMA helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ gather-MMA kernel
+// 8 consumer warps (each MT x 16 output rows) + 1 producer warp that streams the per-step weight blocks through a
+// ring of shared-memory stages with TMA bulk copies. Consumers never meet at a block barrier: they wait on the stage's
+// "full" mbarrier, multiply, and release it on the "empty" mbarrier; the gather of step s+1 is in flight while step s
+// is multiplied.
 constexpr int kConvWarps = 8;
-constexpr int kConvThreads = kConvWarps * 32;
+constexpr int kConvThreads = (kConvWarps + 1) * 32;
+constexpr int kMaxStages = 4;
+
+// resident CTAs per SM the register allocation aims for (9 warps per CTA)
+constexpr int conv_min_blocks(int mt, int np, bool split) { return split ? 1 : (mt * np <= 2 ? 3 : (mt * np <= 6 ? 2 : 1)); }
 
 template <int MT, int NP, bool SPLIT>
-__global__ void __launch_bounds__(kConvThreads) k_gather_mma(Gather gt, const float *__restrict__ in, int64_t ld_in,
+__global__ void __launch_bounds__(kConvThreads, conv_min_blocks(MT, NP, SPLIT)) k_gather_mma(Gather gt, const float *__restrict__ in, int64_t ld_in,
                                                              float *__restrict__ out, int64_t ld_out,
-                                                             const float *__restrict__ packed, int c_in, int kc) {
+                                                             const float *__restrict__ packed, int c_in, int n_stages) {
     constexpr int TM = kConvWarps * MT * 16;  // output rows per CTA
     constexpr int C_OUT = NP * 16;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int H = SPLIT ? 2 : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = gt.volume;
-    int32_t *sT = reinterpret_cast<int32_t *>(smem_raw);               // [K][TM]
-    int32_t *sActive = sT + K * TM;                                    // [32] active offsets, [32] = count
-    float *sW = reinterpret_cast<float *>(sActive + 40);               // 2 stages
-    const int stage_floats = kc * C_OUT * (SPLIT ? 2 : 1);
-    const int nchunk = c_in / kc;
+    float *sW = reinterpret_cast<float *>(smem_raw);  // n_stages x (kChunk * C_OUT * H) floats, 128-byte aligned
+    const int stage_floats = kChunk * C_OUT * H;
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(sW + (int64_t)n_stages * stage_floats);
+    uint64_t *bar_empty = bar_full + kMaxStages;
+    int32_t *sActive = reinterpret_cast<int32_t *>(bar_empty + kMaxStages);  // [32] active offsets, [32] = count
+    int32_t *sT = sActive + 40;                                             // [K][TM]
+    const int nchunk = (c_in + kChunk - 1) / kChunk;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -114,6 +154,13 @@ __global__ void __launch_bounds__(kConvThreads) k_gather_mma(Gather gt, const fl
 
     // ---- stage the tile's slice of the gather table; find the offsets that touch this tile
     if (tid < 40) sActive[tid] = 0;
+    if (tid == 0) {
+        for (int i = 0; i < n_stages; ++i) {
+            mbar_init(bar_full + i, 1);
+            mbar_init(bar_empty + i, kConvWarps);
+        }
+        mbar_fence_init();
+    }
     __syncthreads();
     for (int idx = tid; idx < K * TM; idx += kConvThreads) {
         const int k = idx / TM, r = idx - k * TM;
@@ -130,9 +177,24 @@ __global__ void __launch_bounds__(kConvThreads) k_gather_mma(Gather gt, const fl
         if (on) sActive[__popc(m & ((1u << lane) - 1))] = lane;
         if (lane == 0) sActive[32] = __popc(m);
     }
-    __syncthreads();
-    const int n_act = sActive[32];
-    const int n_steps = n_act * nchunk;
+    __syncthreads();  // last block-wide barrier: the producer warp leaves early
+    const int n_steps = sActive[32] * nchunk;
+
+    if (warp == kConvWarps) {  // ===== producer: one lane feeds the ring =====
+        if (lane == 0) {
+            for (int step = 0; step < n_steps; ++step) {
+                const int slot = step % n_stages, use = step / n_stages;
+                const int a = step / nchunk, ch = step - a * nchunk;
+                const int kc = min(kChunk, c_in - ch * kChunk);
+                const uint32_t bytes = (uint32_t)kc * C_OUT * H * 4;
+                const float *src = packed + ((int64_t)sActive[a] * c_in + ch * kChunk) * C_OUT * H;
+                mbar_wait(bar_empty + slot, (use & 1) ^ 1);
+                mbar_expect_tx(bar_full + slot, bytes);
+                tma_load_1d(sW + (int64_t)slot * stage_floats, src, bytes, bar_full + slot);
+            }
+        }
+        return;
+    }
 
     float acc[MT][2 * NP][4];
 #pragma unroll
@@ -142,82 +204,95 @@ __global__ void __launch_bounds__(kConvThreads) k_gather_mma(Gather gt, const fl
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[m][p][e] = 0.f;
 
-    auto prefetch = [&](int step, int buf) {
-        const int k = sActive[step / nchunk], ch = step - (step / nchunk) * nchunk;
-        const float *src = packed + ((int64_t)k * nchunk + ch) * stage_floats;
-        float *dst = sW + (int64_t)buf * stage_floats;
-        for (int i = tid * 4; i < stage_floats; i += kConvThreads * 4) cp_async16(dst + i, src + i, true);
-        cp_async_commit();
+    const int warp_row = warp * MT * 16;
+    const float *abase = in + 4 * t;
+
+    // gather the A rows of one step (up to 32 channels = two float4 per row half); rows without a rule stay zero
+    auto load_a = [&](int step, float4 (&x)[MT][2][2], bool &any) {
+        any = false;
+        if (step >= n_steps) return;
+        const int a = step / nchunk, ch = step - a * nchunk;
+        const int k = sActive[a];
+        const int nj = min(kChunk, c_in - ch * kChunk) / 16;
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int idx = sT[k * TM + warp_row + m * 16 + g + 8 * h];
+                any |= idx >= 0;
+                const float *p = abase + (int64_t)idx * ld_in + ch * kChunk;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    x[m][h][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (idx >= 0 && j < nj) x[m][h][j] = __ldg(reinterpret_cast<const float4 *>(p + 16 * j));
+                }
+            }
+        any = __any_sync(0xffffffffu, any);
     };
 
-    if (n_steps > 0) prefetch(0, 0);
-    const int warp_row = warp * MT * 16;
-
-    for (int step = 0; step < n_steps; ++step) {
-        cp_async_wait<0>();
-        __syncthreads();
-        if (step + 1 < n_steps) prefetch(step + 1, (step + 1) & 1);
-        const int k = sActive[step / nchunk], ch = step - (step / nchunk) * nchunk;
-        const float *w = sW + (int64_t)(step & 1) * stage_floats;
-
-        int idx[MT][2];
-        bool any = false;
+    auto compute = [&](int step, const float4 (&x)[MT][2][2], bool any) {
+        const int slot = step % n_stages, use = step / n_stages;
+        mbar_wait(bar_full + slot, use & 1);
+        if (any) {
+            const int ch = step % nchunk;
+            const int kc = min(kChunk, c_in - ch * kChunk);
+            const float4 *w = reinterpret_cast<const float4 *>(sW + (int64_t)slot * stage_floats) + lane;
+            const int lo_off = (kc / 8) * NP * 32;  // float4 offset of the lo half (split mode)
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            idx[m][0] = sT[k * TM + warp_row + m * 16 + g];
-            idx[m][1] = sT[k * TM + warp_row + m * 16 + g + 8];
-            any |= (idx[m][0] >= 0) | (idx[m][1] >= 0);
-        }
-        if (!__any_sync(0xffffffffu, any)) continue;
-
-        const float *abase = in + (int64_t)ch * kc + 4 * t;
-        for (int j = 0; j < kc / 16; ++j) {
-            float4 x[MT][2];
+            for (int j = 0; j < 2; ++j) {
+                if (j * 16 >= kc) break;
 #pragma unroll
-            for (int m = 0; m < MT; ++m)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    x[m][h] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (idx[m][h] >= 0)
-                        x[m][h] = __ldg(reinterpret_cast<const float4 *>(abase + (int64_t)idx[m][h] * ld_in + 16 * j));
-                }
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                uint32_t a_hi[MT][4], a_lo[MT][4];
-#pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                    const float v0 = e ? x[m][0].z : x[m][0].x, v2 = e ? x[m][0].w : x[m][0].y;
-                    const float v1 = e ? x[m][1].z : x[m][1].x, v3 = e ? x[m][1].w : x[m][1].y;
-                    a_hi[m][0] = to_tf32(v0); a_hi[m][1] = to_tf32(v1); a_hi[m][2] = to_tf32(v2); a_hi[m][3] = to_tf32(v3);
-                    if (SPLIT) {
-                        a_lo[m][0] = to_tf32(v0 - __uint_as_float(a_hi[m][0]));
-                        a_lo[m][1] = to_tf32(v1 - __uint_as_float(a_hi[m][1]));
-                        a_lo[m][2] = to_tf32(v2 - __uint_as_float(a_hi[m][2]));
-                        a_lo[m][3] = to_tf32(v3 - __uint_as_float(a_hi[m][3]));
-                    }
-                }
-                const int s = 2 * j + e;
-                const float4 *wf = reinterpret_cast<const float4 *>(w) + ((int64_t)s * NP) * 32 + lane;
-#pragma unroll
-                for (int u = 0; u < NP; ++u) {
-                    const float4 b = wf[u * 32];
-                    if (SPLIT) {
-                        const float4 bl = wf[(int64_t)(kc / 8) * NP * 32 + u * 32];
-#pragma unroll
-                        for (int m = 0; m < MT; ++m) {
-                            mma_tf32(acc[m][2 * u], a_lo[m], __float_as_uint(b.x), __float_as_uint(b.y));
-                            mma_tf32(acc[m][2 * u + 1], a_lo[m], __float_as_uint(b.z), __float_as_uint(b.w));
-                            mma_tf32(acc[m][2 * u], a_hi[m], __float_as_uint(bl.x), __float_as_uint(bl.y));
-                            mma_tf32(acc[m][2 * u + 1], a_hi[m], __float_as_uint(bl.z), __float_as_uint(bl.w));
-                        }
-                    }
+                for (int e = 0; e < 2; ++e) {
+                    uint32_t a_hi[MT][4], a_lo[MT][4];
 #pragma unroll
                     for (int m = 0; m < MT; ++m) {
-                        mma_tf32(acc[m][2 * u], a_hi[m], __float_as_uint(b.x), __float_as_uint(b.y));
-                        mma_tf32(acc[m][2 * u + 1], a_hi[m], __float_as_uint(b.z), __float_as_uint(b.w));
+                        const float v0 = e ? x[m][0][j].z : x[m][0][j].x, v2 = e ? x[m][0][j].w : x[m][0][j].y;
+                        const float v1 = e ? x[m][1][j].z : x[m][1][j].x, v3 = e ? x[m][1][j].w : x[m][1][j].y;
+                        a_hi[m][0] = to_tf32(v0); a_hi[m][1] = to_tf32(v1); a_hi[m][2] = to_tf32(v2); a_hi[m][3] = to_tf32(v3);
+                        if (SPLIT) {
+                            a_lo[m][0] = to_tf32(v0 - __uint_as_float(a_hi[m][0]));
+                            a_lo[m][1] = to_tf32(v1 - __uint_as_float(a_hi[m][1]));
+                            a_lo[m][2] = to_tf32(v2 - __uint_as_float(a_hi[m][2]));
+                            a_lo[m][3] = to_tf32(v3 - __uint_as_float(a_hi[m][3]));
+                        }
+                    }
+                    const float4 *wf = w + (2 * j + e) * NP * 32;
+#pragma unroll
+                    for (int u = 0; u < NP; ++u) {
+                        const float4 b = wf[u * 32];
+                        if (SPLIT) {
+                            const float4 bl = wf[lo_off + u * 32];
+#pragma unroll
+                            for (int m = 0; m < MT; ++m) {
+                                mma_tf32(acc[m][2 * u], a_lo[m], __float_as_uint(b.x), __float_as_uint(b.y));
+                                mma_tf32(acc[m][2 * u + 1], a_lo[m], __float_as_uint(b.z), __float_as_uint(b.w));
+                                mma_tf32(acc[m][2 * u], a_hi[m], __float_as_uint(bl.x), __float_as_uint(bl.y));
+                                mma_tf32(acc[m][2 * u + 1], a_hi[m], __float_as_uint(bl.z), __float_as_uint(bl.w));
+                            }
+                        }
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) {
+                            mma_tf32(acc[m][2 * u], a_hi[m], __float_as_uint(b.x), __float_as_uint(b.y));
+                            mma_tf32(acc[m][2 * u + 1], a_hi[m], __float_as_uint(b.z), __float_as_uint(b.w));
+                        }
                     }
                 }
             }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + slot);
+    };
+
+    // two register sets ping-pong: while set A is multiplied, set B's gathers are in flight
+    float4 xa[MT][2][2], xb[MT][2][2];
+    bool any_a = false, any_b = false;
+    load_a(0, xa, any_a);
+    for (int step = 0; step < n_steps; step += 2) {
+        load_a(step + 1, xb, any_b);
+        compute(step, xa, any_a);
+        if (step + 1 < n_steps) {
+            load_a(step + 2, xa, any_a);
+            compute(step + 1, xb, any_b);
         }
     }
 
@@ -227,13 +302,53 @@ __global__ void __launch_bounds__(kConvThreads) k_gather_mma(Gather gt, const fl
         const int64_t r_lo = row0 + warp_row + m * 16 + g, r_hi = r_lo + 8;
 #pragma unroll
         for (int u = 0; u < NP; ++u) {
-            if (r_lo < gt.n_out)
-                *reinterpret_cast<float4 *>(out + r_lo * ld_out + 16 * u + 4 * t) =
-                    make_float4(acc[m][2 * u][0], acc[m][2 * u][1], acc[m][2 * u + 1][0], acc[m][2 * u + 1][1]);
-            if (r_hi < gt.n_out)
-                *reinterpret_cast<float4 *>(out + r_hi * ld_out + 16 * u + 4 * t) =
-                    make_float4(acc[m][2 * u][2], acc[m][2 * u][3], acc[m][2 * u + 1][2], acc[m][2 * u + 1][3]);
+            if (r_lo < gt.n_out) {
+                float4 *dst = reinterpret_cast<float4 *>(out + r_lo * ld_out + 16 * u + 4 * t);
+                float4 v = make_float4(acc[m][2 * u][0], acc[m][2 * u][1], acc[m][2 * u + 1][0], acc[m][2 * u + 1][1]);
+                if (gt.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                *dst = v;
+            }
+            if (r_hi < gt.n_out) {
+                float4 *dst = reinterpret_cast<float4 *>(out + r_hi * ld_out + 16 * u + 4 * t);
+                float4 v = make_float4(acc[m][2 * u][2], acc[m][2 * u][3], acc[m][2 * u + 1][2], acc[m][2 * u + 1][3]);
+                if (gt.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                *dst = v;
+            }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ small-c_in conv
+// The 1 -> 16 input layer (scn_unet.py:27): one thread per output row and block of 16 output channels, weights in
+// shared memory, table reads coalesced across the warp. out[o][co] = sum_k sum_ci in[T[k][o]][ci] * W[k][ci][co].
+__global__ void __launch_bounds__(256) k_conv_smallcin(Gather gt, const float *__restrict__ in, int64_t ld_in,
+                                                       float *__restrict__ out, int64_t ld_out,
+                                                       const float *__restrict__ w, int c_in, int c_out) {
+    extern __shared__ float sw[];  // [K][c_in][c_out]
+    for (int i = threadIdx.x; i < gt.volume * c_in * c_out; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cb = blockIdx.y * 16;
+    if (o >= gt.n_out) return;
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+    for (int k = 0; k < gt.volume; ++k) {
+        const int i = gather_lookup(gt, k, o);
+        if (i < 0) continue;
+        for (int ci = 0; ci < c_in; ++ci) {
+            const float x = __ldg(in + (int64_t)i * ld_in + ci);
+            const float *wr = sw + (k * c_in + ci) * c_out + cb;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = fmaf(x, wr[c], acc[c]);
+        }
+    }
+    float *dst = out + o * ld_out + cb;
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+        float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+        if (gt.accumulate) { const float4 e = *reinterpret_cast<float4 *>(dst + c); v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
+        *reinterpret_cast<float4 *>(dst + c) = v;
     }
 }
 
@@ -261,7 +376,7 @@ __global__ void __launch_bounds__(256) k_conv_generic(Gather gt, const float *__
             acc = fmaf(__ldg(row + ci), wv, acc);
         }
     }
-    out[o * ld_out + co] = acc;
+    out[o * ld_out + co] = gt.accumulate ? out[o * ld_out + co] + acc : acc;
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
@@ -496,7 +611,7 @@ __global__ void __launch_bounds__(256) k_dw_reduce(const float *__restrict__ par
 }
 
 // ------------------------------------------------------------------------------------------------ host dispatch
-static bool mma_shape_ok(int c_in, int c_out) {
+bool conv_uses_packed(int c_in, int c_out) {
     if (c_in % 16 || c_out % 16 || c_in < 16 || c_out < 16) return false;
     const int np = c_out / 16;
     return np <= 8 || np == 10 || np == 12;
@@ -507,12 +622,22 @@ template <int MT, int NP, bool SPLIT>
 static int launch_gather_mma(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out,
                              const float *packed, int c_in, cudaStream_t s) {
     constexpr int TM = kConvWarps * MT * 16;
-    const int kc = choose_kc(c_in, NP * 16, SPLIT);
-    const size_t smem = (size_t)gt.volume * TM * 4 + 40 * 4 + (size_t)2 * kc * NP * 16 * (SPLIT ? 2 : 1) * 4;
+    const size_t stage = (size_t)kChunk * NP * 16 * (SPLIT ? 2 : 1) * 4;
+    const size_t fixed = (size_t)2 * kMaxStages * 8 + 40 * 4 + (size_t)gt.volume * TM * 4;
+    int stages = kMaxStages;
+    while (stages > 2 && stages * stage + fixed > 72 * 1024) --stages;  // keep three CTAs per SM where possible
+    const int nsteps_max = gt.volume * (int)ceil_div(c_in, kChunk);
+    if (stages > nsteps_max) stages = nsteps_max < 1 ? 1 : nsteps_max;
+    const size_t smem = stages * stage + fixed;
     auto kern = k_gather_mma<MT, NP, SPLIT>;
-    MOPA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool configured = false;  // per template instantiation
+    if (!configured) {
+        MOPA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MOPA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured = true;
+    }
     const unsigned grid = (unsigned)ceil_div(gt.n_out, TM);
-    kern<<<grid, kConvThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, kc);
+    kern<<<grid, kConvThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, stages);
     MOPA_LAUNCHED();
     return 0;
 }
@@ -521,7 +646,7 @@ template <int NP>
 static int dispatch_np(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out,
                        const float *packed, int c_in, int split, cudaStream_t s) {
     // two m-tiles per warp (B fragments re-used twice) while the accumulators fit and the grid still fills the chip
-    const bool wide_tile = NP <= 4 && gt.n_out >= (int64_t)2 * kNumSMs * 256;
+    const bool wide_tile = false;  // measured: the second m-tile costs more occupancy than the B re-use saves
     if (split) return launch_gather_mma<1, NP, true>(gt, in, ld_in, out, ld_out, packed, c_in, s);
     if (wide_tile) return launch_gather_mma<(NP <= 4 ? 2 : 1), NP, false>(gt, in, ld_in, out, ld_out, packed, c_in, s);
     return launch_gather_mma<1, NP, false>(gt, in, ld_in, out, ld_out, packed, c_in, s);
@@ -532,8 +657,15 @@ int conv_apply(const Gather &gt, const float *in, int64_t ld_in, float *out, int
                const float *packed, int n_in0, int n_out0, int transpose, int flip, int precision, cudaStream_t s) {
     if (gt.n_out == 0) return 0;
     const int c_in = transpose ? n_out0 : n_in0, c_out = transpose ? n_in0 : n_out0;
-    const bool fast = mma_shape_ok(c_in, c_out) && packed && aligned16(in) && aligned16(out) && ld_in % 4 == 0 &&
+    const bool fast = conv_uses_packed(c_in, c_out) && packed && aligned16(in) && aligned16(out) && ld_in % 4 == 0 &&
                       ld_out % 4 == 0 && aligned16(packed);
+    if (!fast && !transpose && !flip && c_in <= 8 && c_out % 16 == 0 && (size_t)gt.volume * c_in * c_out * 4 <= 40 * 1024 &&
+        weight && aligned16(out) && ld_out % 4 == 0) {
+        dim3 grid((unsigned)ceil_div(gt.n_out, 256), c_out / 16);
+        k_conv_smallcin<<<grid, 256, (size_t)gt.volume * c_in * c_out * 4, s>>>(gt, in, ld_in, out, ld_out, weight, c_in, c_out);
+        MOPA_LAUNCHED();
+        return 0;
+    }
     if (!fast) {
         MOPA_CHECK(weight != nullptr, "generic conv path needs the unpacked weight");
         const int64_t total = gt.n_out * c_out;
@@ -565,7 +697,8 @@ struct DwPlan {
 };
 static DwPlan dw_plan(int volume, int n_in, int n_out, int64_t n_rows) {
     DwPlan p{};
-    p.mma = n_in % 16 == 0 && n_out % 16 == 0 && n_in >= 16 && n_out >= 16 && n_in <= 256 && n_out <= 256;
+    p.mma = n_in % 16 == 0 && n_out % 16 == 0 && n_in >= 16 && n_out >= 16 &&
+            ((n_in + 31) / 32) * ((n_out + 31) / 32) <= 32;
     int nch = (int)ceil_div(n_rows > 0 ? n_rows : 1, 512);
     p.nchunks = nch < 1 ? 1 : (nch > 32 ? 32 : nch);
     p.rows_per_chunk = (int)round_up(ceil_div(n_rows > 0 ? n_rows : 1, p.nchunks), 4);
@@ -592,7 +725,12 @@ static int launch_dw(const Gather &gt, const float *in, int64_t ld_in, const flo
                      int n_out, const DwPlan &p, float *partial, int center, cudaStream_t s) {
     const size_t smem = (size_t)(2 * kDwSub + 16) * 4 + (size_t)2 * p.RT * (n_in + 8 + n_out + 8) * 4;
     auto kern = k_dw_mma<BPW, SPLIT>;
-    MOPA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool configured = false;
+    if (!configured) {
+        MOPA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MOPA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured = true;
+    }
     dim3 grid(p.nchunks, gt.volume);
     kern<<<grid, kDwThreads, smem, s>>>(gt, in, ld_in, dout, ld_dout, n_in, n_out, p.rows_per_chunk, p.RT, p.WK, partial,
                                         center);
@@ -613,9 +751,6 @@ int conv_dweight(const Gather &gt, const float *in, int64_t ld_in, const float *
     float *partial = reinterpret_cast<float *>(workspace);
     const bool fast = p.mma && aligned16(in) && aligned16(dout) && ld_in % 4 == 0 && ld_dout % 4 == 0;
     if (fast) {
-        // warps that own no (block, k-step) slot leave their slice untouched: clear when the 8 warps are not all used
-        const int nblk = ((n_in + 31) / 32) * ((n_out + 31) / 32);
-        if (nblk < 8 && nblk * p.WK < 8) { /* slices are indexed by wk < WK only: all written */ }
         const int center = gt.volume == 27 && gt.table ? 13 : -1;
         const bool split = precision == MOPA_SCN_PREC_FP32;
 #define MOPA_DW(B)                                                                                            \
@@ -626,10 +761,6 @@ int conv_dweight(const Gather &gt, const float *in, int64_t ld_in, const float *
             case 2: MOPA_TRY(MOPA_DW(2)); break;
             case 3: MOPA_TRY(MOPA_DW(3)); break;
             case 4: MOPA_TRY(MOPA_DW(4)); break;
-            case 5: MOPA_TRY(MOPA_DW(5)); break;
-            case 6: MOPA_TRY(MOPA_DW(6)); break;
-            case 7: MOPA_TRY(MOPA_DW(7)); break;
-            case 8: MOPA_TRY(MOPA_DW(8)); break;
             default: MOPA_FAIL("d_weight: channel counts too large");
         }
 #undef MOPA_DW
@@ -646,6 +777,34 @@ int conv_dweight(const Gather &gt, const float *in, int64_t ld_in, const float *
     return 0;
 }
 
+int pack_weights(const float *weight, int volume, int n_in, int n_out, int transpose, int flip, int precision,
+                 float *packed, cudaStream_t s) {
+    const int c_in = transpose ? n_out : n_in, c_out = transpose ? n_in : n_out;
+    MOPA_CHECK(c_in % 16 == 0 && c_out % 16 == 0, "packWeights: channel counts must be multiples of 16");
+    const int split = precision == MOPA_SCN_PREC_FP32;
+    const int64_t total = (int64_t)volume * n_in * n_out * (split ? 2 : 1);
+    k_pack_weights<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(weight, volume, n_in, n_out, transpose, flip, split, packed,
+                                                                  total);
+    MOPA_LAUNCHED();
+    return 0;
+}
+
+Gather subm_gather(const Level &L) {
+    Gather g;
+    g.table = L.nbr; g.ld = L.nbr_ld; g.volume = 27; g.n_out = L.V; g.n_in = L.V;
+    return g;
+}
+Gather child_gather(const Level &fine, const Level &coarse) {  // rows = coarse sites, inputs = fine sites
+    Gather g;
+    g.table = fine.child; g.ld = fine.child_ld; g.volume = 8; g.n_out = coarse.V; g.n_in = fine.V;
+    return g;
+}
+Gather select_gather(const Level &fine, const Level &coarse) {  // rows = fine sites, inputs = coarse sites
+    Gather g;
+    g.parent = fine.parent; g.kidx = fine.kidx; g.volume = 8; g.n_out = fine.V; g.n_in = coarse.V;
+    return g;
+}
+
 }  // namespace mopa
 
 using namespace mopa;
@@ -658,15 +817,7 @@ int64_t mopa_scn_packedWeightFloats(int volume, int n_in, int n_out, int precisi
 
 int mopa_scn_packWeights(const float *weight, int volume, int n_in, int n_out, int transpose, int flip, int precision,
                          float *packed, void *stream) {
-    const int c_in = transpose ? n_out : n_in, c_out = transpose ? n_in : n_out;
-    MOPA_CHECK(c_in % 16 == 0 && c_out % 16 == 0, "packWeights: channel counts must be multiples of 16");
-    const int split = precision == MOPA_SCN_PREC_FP32;
-    const int kc = choose_kc(c_in, c_out, split);
-    const int64_t total = mopa_scn_packedWeightFloats(volume, n_in, n_out, precision);
-    k_pack_weights<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(weight, volume, n_in, n_out, transpose,
-                                                                                     flip, split, kc, packed, total);
-    MOPA_LAUNCHED();
-    return 0;
+    return pack_weights(weight, volume, n_in, n_out, transpose, flip, precision, packed, (cudaStream_t)stream);
 }
 
 size_t mopa_scn_backwardWorkspaceBytes(int volume, int n_in, int n_out, int64_t n_rows) {
@@ -678,22 +829,6 @@ static int get_level(mopa_scn_metadata *m, int64_t spatial, int &l) {
     l = m->level_of(spatial);
     MOPA_CHECK(l >= 0, "no grid at this spatial size");
     return 0;
-}
-
-static Gather subm_gather(const Level &L) {
-    Gather g;
-    g.table = L.nbr; g.ld = L.nbr_ld; g.volume = 27; g.n_out = L.V; g.n_in = L.V;
-    return g;
-}
-static Gather child_gather(const Level &fine, const Level &coarse) {  // rows = coarse sites, inputs = fine sites
-    Gather g;
-    g.table = fine.child; g.ld = fine.child_ld; g.volume = 8; g.n_out = coarse.V; g.n_in = fine.V;
-    return g;
-}
-static Gather select_gather(const Level &fine, const Level &coarse) {  // rows = fine sites, inputs = coarse sites
-    Gather g;
-    g.parent = fine.parent; g.kidx = fine.kidx; g.volume = 8; g.n_out = fine.V; g.n_in = coarse.V;
-    return g;
 }
 
 int mopa_scn_SubmanifoldConvolution_updateOutput(mopa_scn_metadata *m, int64_t spatial_size, int filter_size,

@@ -289,12 +289,6 @@ __global__ void __launch_bounds__(256) k_csr_order(const int32_t *__restrict__ p
     rows[beg + r] = (int32_t)i;
 }
 
-__global__ void k_set_last(int32_t *off, int64_t v_bound, const int32_t *count_dev, int32_t n) {
-    // off[V] = n where V = *count_dev
-    (void)v_bound;
-    off[*count_dev] = n;
-}
-
 // ------------------------------------------------------------------------------------------------ submanifold table
 // grid (ceil(V / 256), 27): one thread per (offset, site); writes are coalesced along the site axis.
 __global__ void __launch_bounds__(256) k_subm_table(const uint64_t *__restrict__ keys, int64_t V, int spatial,
@@ -446,6 +440,68 @@ static int rulebook_to_host(mopa_scn_metadata *m, const int32_t *table, int64_t 
     return 0;
 }
 
+int set_locations(mopa_scn_metadata *m, int64_t spatial_size, const int64_t *coords, int64_t n, int ncols,
+                  int coords_on_device, cudaStream_t s) {
+    MOPA_CHECK(m != nullptr, "null metadata");
+    MOPA_CHECK(ncols == 3 || ncols == 4, "coords must have 3 or 4 columns");
+    MOPA_CHECK(spatial_size > 0 && spatial_size <= 65536, "spatial_size must be in (0, 65536]");
+    MOPA_CHECK(m->levels.empty(), "setLocations called twice on one Metadata");
+    MOPA_CHECK(n >= 0 && n < (int64_t)1 << 30, "point count out of range");
+    MOPA_CUDA(cudaSetDevice(m->device));
+    m->levels.emplace_back();
+    Level &L = m->levels[0];
+    L.spatial = spatial_size;
+    m->n_points = n;
+
+    const int64_t *dcoords = coords;
+    int64_t *staged = nullptr;
+    if ((!coords_on_device || ((uintptr_t)coords & 15) != 0) && n > 0) {
+        MOPA_TRY(tmp_alloc((void **)&staged, (size_t)n * ncols * 8, s));
+        MOPA_CUDA(cudaMemcpyAsync(staged, coords, (size_t)n * ncols * 8,
+                                  coords_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        dcoords = staged;
+    }
+    L.cap = table_capacity(n);
+    MOPA_TRY(meta_alloc(m, (void **)&L.tab_keys, (size_t)L.cap * 8, s));
+    MOPA_TRY(meta_alloc(m, (void **)&L.tab_vals, (size_t)L.cap * 4, s));
+    MOPA_TRY(meta_alloc(m, (void **)&L.keys, (size_t)n * 8, s));
+    MOPA_TRY(meta_alloc(m, (void **)&m->p2v, (size_t)n * 4, s));
+    MOPA_TRY(meta_alloc(m, (void **)&m->csr_off, (size_t)(n + 1) * 4, s));
+    MOPA_TRY(meta_alloc(m, (void **)&m->csr_rows, (size_t)n * 4, s));
+    int32_t *counts, *cnt, *tmp_rows, *bsum;
+    MOPA_TRY(tmp_alloc((void **)&counts, (size_t)(n + 1) * 4, s));
+    MOPA_TRY(tmp_alloc((void **)&cnt, 8, s));
+    MOPA_TRY(tmp_alloc((void **)&tmp_rows, (size_t)n * 4, s));
+    MOPA_TRY(tmp_alloc((void **)&bsum, (size_t)ceil_div(n + 1, 1024) * 4, s));
+    MOPA_CUDA(cudaMemsetAsync(counts, 0, (size_t)(n + 1) * 4, s));
+    MOPA_CUDA(cudaMemsetAsync(cnt, 0, 8, s));
+    MOPA_TRY(unique_first(0, dcoords, ncols, spatial_size, nullptr, n, L.tab_keys, L.tab_vals, L.cap, L.keys, m->p2v,
+                          nullptr, counts, cnt, cnt + 1, s));
+    if (n > 0) {
+        // CSR offsets over the (n + 1)-long zero-padded count array: off[v] valid for v <= V0, off[V0] = n
+        MOPA_TRY(exclusive_scan(counts, m->csr_off, n + 1, bsum, nullptr, s));
+        MOPA_CUDA(cudaMemsetAsync(counts, 0, (size_t)n * 4, s));  // reuse as per-voxel cursor
+        unsigned g = (unsigned)ceil_div(n, 256);
+        k_csr_fill<<<g, 256, 0, s>>>(m->p2v, m->csr_off, n, counts, tmp_rows);
+        MOPA_LAUNCHED();
+        k_csr_order<<<g, 256, 0, s>>>(m->p2v, m->csr_off, tmp_rows, n, m->csr_rows);
+        MOPA_LAUNCHED();
+    } else {
+        MOPA_CUDA(cudaMemsetAsync(m->csr_off, 0, 4, s));
+    }
+    MOPA_TRY(read_back(m, cnt, 2, s));
+    L.V = m->pinned[0];
+    int err = m->pinned[1];
+    MOPA_CUDA(cudaFreeAsync(counts, s));
+    MOPA_CUDA(cudaFreeAsync(cnt, s));
+    MOPA_CUDA(cudaFreeAsync(tmp_rows, s));
+    MOPA_CUDA(cudaFreeAsync(bsum, s));
+    if (staged) MOPA_CUDA(cudaFreeAsync(staged, s));
+    MOPA_CHECK(err == 0, "InputLayer: coordinates outside [0, spatial_size) or batch index outside [0, 65535)");
+    return 0;
+}
+
+
 }  // namespace mopa
 
 using namespace mopa;
@@ -488,6 +544,7 @@ void mopa_scn_Metadata_delete(mopa_scn_metadata *m) {
     cudaGetDevice(&prev);
     cudaSetDevice(m->device);
     for (void *p : m->allocs) cudaFreeAsync(p, m->last_stream);
+    if (m->geom_done) cudaEventDestroy(m->geom_done);
     cudaSetDevice(prev);
     pin_put(m->pinned);
     delete m;
@@ -497,63 +554,9 @@ int mopa_scn_InputLayer_setLocations(mopa_scn_metadata *m, int64_t spatial_size,
                                      int ncols, int coords_on_device, int mode, void *stream, int64_t *n_active_out) {
     MOPA_CHECK(m != nullptr, "null metadata");
     MOPA_CHECK(mode == 4, "only InputLayer mode 4 (mean) is implemented (scn_unet.py:26)");
-    MOPA_CHECK(ncols == 3 || ncols == 4, "coords must have 3 or 4 columns");
-    MOPA_CHECK(spatial_size > 0 && spatial_size <= 65536, "spatial_size must be in (0, 65536]");
-    MOPA_CHECK(m->levels.empty(), "setLocations called twice on one Metadata");
-    MOPA_CHECK(n >= 0 && n < (int64_t)1 << 30, "point count out of range");
-    cudaStream_t s = (cudaStream_t)stream;
-    m->last_stream = s;
-    MOPA_CUDA(cudaSetDevice(m->device));
-    m->levels.emplace_back();
-    Level &L = m->levels[0];
-    L.spatial = spatial_size;
-    m->n_points = n;
-
-    const int64_t *dcoords = coords;
-    int64_t *staged = nullptr;
-    if (!coords_on_device && n > 0) {
-        MOPA_TRY(tmp_alloc((void **)&staged, (size_t)n * ncols * 8, s));
-        MOPA_CUDA(cudaMemcpyAsync(staged, coords, (size_t)n * ncols * 8, cudaMemcpyHostToDevice, s));
-        dcoords = staged;
-    }
-    L.cap = table_capacity(n);
-    MOPA_TRY(meta_alloc(m, (void **)&L.tab_keys, (size_t)L.cap * 8, s));
-    MOPA_TRY(meta_alloc(m, (void **)&L.tab_vals, (size_t)L.cap * 4, s));
-    MOPA_TRY(meta_alloc(m, (void **)&L.keys, (size_t)n * 8, s));
-    MOPA_TRY(meta_alloc(m, (void **)&m->p2v, (size_t)n * 4, s));
-    MOPA_TRY(meta_alloc(m, (void **)&m->csr_off, (size_t)(n + 1) * 4, s));
-    MOPA_TRY(meta_alloc(m, (void **)&m->csr_rows, (size_t)n * 4, s));
-    int32_t *counts, *cnt, *tmp_rows, *bsum;
-    MOPA_TRY(tmp_alloc((void **)&counts, (size_t)(n + 1) * 4, s));
-    MOPA_TRY(tmp_alloc((void **)&cnt, 8, s));
-    MOPA_TRY(tmp_alloc((void **)&tmp_rows, (size_t)n * 4, s));
-    MOPA_TRY(tmp_alloc((void **)&bsum, (size_t)ceil_div(n + 1, 1024) * 4, s));
-    MOPA_CUDA(cudaMemsetAsync(counts, 0, (size_t)(n + 1) * 4, s));
-    MOPA_CUDA(cudaMemsetAsync(cnt, 0, 8, s));
-    MOPA_TRY(unique_first(0, dcoords, ncols, spatial_size, nullptr, n, L.tab_keys, L.tab_vals, L.cap, L.keys, m->p2v,
-                          nullptr, counts, cnt, cnt + 1, s));
-    if (n > 0) {
-        // CSR offsets over the (n + 1)-long zero-padded count array: off[v] valid for v <= V0, off[V0] = n
-        MOPA_TRY(exclusive_scan(counts, m->csr_off, n + 1, bsum, nullptr, s));
-        MOPA_CUDA(cudaMemsetAsync(counts, 0, (size_t)n * 4, s));  // reuse as per-voxel cursor
-        unsigned g = (unsigned)ceil_div(n, 256);
-        k_csr_fill<<<g, 256, 0, s>>>(m->p2v, m->csr_off, n, counts, tmp_rows);
-        MOPA_LAUNCHED();
-        k_csr_order<<<g, 256, 0, s>>>(m->p2v, m->csr_off, tmp_rows, n, m->csr_rows);
-        MOPA_LAUNCHED();
-    } else {
-        MOPA_CUDA(cudaMemsetAsync(m->csr_off, 0, 4, s));
-    }
-    MOPA_TRY(read_back(m, cnt, 2, s));
-    L.V = m->pinned[0];
-    int err = m->pinned[1];
-    MOPA_CUDA(cudaFreeAsync(counts, s));
-    MOPA_CUDA(cudaFreeAsync(cnt, s));
-    MOPA_CUDA(cudaFreeAsync(tmp_rows, s));
-    MOPA_CUDA(cudaFreeAsync(bsum, s));
-    if (staged) MOPA_CUDA(cudaFreeAsync(staged, s));
-    MOPA_CHECK(err == 0, "InputLayer: coordinates outside [0, spatial_size) or batch index outside [0, 65535)");
-    if (n_active_out) *n_active_out = L.V;
+    m->last_stream = (cudaStream_t)stream;
+    MOPA_TRY(set_locations(m, spatial_size, coords, n, ncols, coords_on_device, (cudaStream_t)stream));
+    if (n_active_out) *n_active_out = m->levels[0].V;
     return 0;
 }
 

@@ -36,6 +36,7 @@ struct mopa_scn_metadata {
     std::vector<void *> allocs;
     cudaStream_t last_stream = nullptr;
     int32_t *pinned = nullptr;  // small host staging block for counts
+    cudaEvent_t geom_done = nullptr;  // recorded on the geometry stream when grids/tables are complete
 
     int level_of(int64_t spatial) const {
         for (size_t l = 0; l < levels.size(); ++l)
@@ -55,9 +56,31 @@ struct Gather {
     int volume = 0;     // 27 or 8
     int64_t n_out = 0;  // output rows
     int64_t n_in = 0;   // input rows (for bounds/debug)
+    int accumulate = 0; // conv_apply: add to the existing output rows instead of overwriting them
 };
 
 int meta_alloc(mopa_scn_metadata *m, void **p, size_t bytes, cudaStream_t s);
+int set_locations(mopa_scn_metadata *m, int64_t spatial_size, const int64_t *coords, int64_t n, int ncols,
+                  int coords_on_device, cudaStream_t s);
+int conv_apply(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *weight,
+               const float *packed, int n_in0, int n_out0, int transpose, int flip, int precision, cudaStream_t s);
+int conv_dweight(const Gather &gt, const float *in, int64_t ld_in, const float *dout, int64_t ld_dout, float *dw,
+                 int n_in, int n_out, int precision, void *workspace, size_t workspace_bytes, cudaStream_t s);
+size_t dw_workspace_bytes(int volume, int n_in, int n_out, int64_t n_rows);
+int pack_weights(const float *weight, int volume, int n_in, int n_out, int transpose, int flip, int precision,
+                 float *packed, cudaStream_t s);
+bool conv_uses_packed(int c_in, int c_out);
+Gather subm_gather(const Level &L);
+Gather child_gather(const Level &fine, const Level &coarse);
+Gather select_gather(const Level &fine, const Level &coarse);
+int bn_forward(const float *in, int64_t ld_in, float *out, int64_t ld_out, float *save_mean, float *save_invstd,
+               float *running_mean, float *running_var, const float *weight, const float *bias, float eps, float momentum,
+               int train, float leakiness, int64_t n_active, int planes, void *workspace, cudaStream_t s);
+int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, const float *d_out, int64_t ld_dout,
+                const float *save_mean, const float *save_invstd, const float *weight, const float *bias, float *d_weight,
+                float *d_bias, float leakiness, int train, int64_t n_active, int planes, void *workspace, int accumulate,
+                cudaStream_t s);
+size_t bn_workspace_bytes(int planes);
 int ensure_subm(mopa_scn_metadata *m, int level, cudaStream_t s);
 int ensure_down(mopa_scn_metadata *m, int level, cudaStream_t s);
 }  // namespace mopa

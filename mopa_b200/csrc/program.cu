@@ -1,0 +1,311 @@
+// Whole-network executor: runs a compiled scn.Sequential (InputLayer ... OutputLayer) forward or backward as ONE
+// C call that enqueues every kernel back to back on the stream.
+//
+// The reference drives SparseConvNet module by module from Python (mopa/models/scn_unet.py:32-34 ->
+// scn.Sequential.forward); at ~90 modules per UNetSCN that costs more host time than the GPU needs for the arithmetic.
+// mopa_b200.scn keeps that module tree (state_dict, .train()/.eval(), deepcopy ...) but compiles it once into the op list
+// executed here. Same kernels as the per-module ABI; additionally
+//   * all grids / neighbour tables of the pyramid are built up front on a dedicated high-priority stream, so the host
+//     synchronisations of the build (one count read-back per level) never wait for the previous step's backward pass;
+//   * JoinTable is free: the joined buffer is allocated once and its producers write straight into column slices;
+//   * gradients that meet at a fan-out are accumulated inside the producing kernels' epilogues.
+#include <map>
+#include <mutex>
+
+#include "geometry.cuh"
+#include "mopa_scn.h"
+
+namespace mopa {
+
+enum { OP_SUBM = 1, OP_CONV = 2, OP_DECONV = 3, OP_BN = 4 };
+constexpr int kOpWidth = 12, kBufWidth = 4;
+
+struct POp {
+    int type, in, out, level_in, level_out, n_in, n_out, param;
+    float leak, eps, momentum;
+};
+struct PBuf {
+    int level, channels, parent, col_off;
+};
+struct Layout {  // resolved per forward from the level sizes
+    std::vector<size_t> buf_off;   // byte offset of root buffers in the activation / gradient arena
+    std::vector<int64_t> buf_ld;   // row stride (floats) of every buffer
+    std::vector<size_t> bn_off;    // per op: byte offset of (save_mean, save_invstd) in the activation arena
+    size_t act_bytes = 0, grad_bytes = 0, packed_bytes = 0, dw_bytes = 0;
+};
+
+static std::mutex g_stream_mu;
+static std::map<int, cudaStream_t> g_geom_streams;
+static int geom_stream(int device, cudaStream_t *out) {
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    auto it = g_geom_streams.find(device);
+    if (it == g_geom_streams.end()) {
+        int lo = 0, hi = 0;
+        MOPA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        cudaStream_t s;
+        MOPA_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
+        it = g_geom_streams.emplace(device, s).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+}  // namespace mopa
+
+struct mopa_scn_program {
+    std::vector<mopa::POp> ops;
+    std::vector<mopa::PBuf> bufs;
+    int in_planes = 0, in_buf = 0, out_buf = 0, n_levels = 1, device = 0;
+    int64_t spatial = 0;
+    void *bn_ws = nullptr;  // persistent, zero-initialised (the BN kernels leave it zeroed)
+};
+
+namespace mopa {
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int make_layout(const mopa_scn_program *p, const mopa_scn_metadata *m, int precision, Layout &L) {
+    MOPA_CHECK((int)m->levels.size() >= p->n_levels, "metadata has fewer levels than the program needs");
+    const size_t nb = p->bufs.size();
+    L.buf_off.assign(nb, 0);
+    L.buf_ld.assign(nb, 0);
+    size_t off = 0;
+    for (size_t b = 0; b < nb; ++b) {
+        const PBuf &B = p->bufs[b];
+        if (B.parent >= 0) continue;
+        L.buf_ld[b] = round_up(B.channels, 4);
+        L.buf_off[b] = off;
+        off += align256((size_t)m->levels[B.level].V * L.buf_ld[b] * 4);
+    }
+    for (size_t b = 0; b < nb; ++b) {
+        const PBuf &B = p->bufs[b];
+        if (B.parent < 0) continue;
+        MOPA_CHECK(p->bufs[B.parent].parent < 0, "nested joins are not supported");
+        L.buf_ld[b] = L.buf_ld[B.parent];
+        L.buf_off[b] = L.buf_off[B.parent] + (size_t)B.col_off * 4;
+    }
+    L.grad_bytes = off + 256;
+    L.bn_off.assign(p->ops.size(), 0);
+    L.packed_bytes = 256;
+    L.dw_bytes = 256;
+    for (size_t i = 0; i < p->ops.size(); ++i) {
+        const POp &o = p->ops[i];
+        if (o.type == OP_BN) {
+            L.bn_off[i] = off;
+            off += align256((size_t)2 * o.n_in * 4);
+        } else {
+            const int volume = o.type == OP_SUBM ? 27 : 8;
+            const size_t pk = (size_t)volume * o.n_in * o.n_out * 4 * (precision == MOPA_SCN_PREC_FP32 ? 2 : 1);
+            if (pk > L.packed_bytes) L.packed_bytes = align256(pk);
+            const int64_t rows = m->levels[o.level_out].V;  // d_weight chunks run over the op's OUTPUT rows
+            const size_t dw = dw_workspace_bytes(volume, o.n_in, o.n_out, rows);
+            if (dw > L.dw_bytes) L.dw_bytes = align256(dw);
+        }
+    }
+    L.act_bytes = off + 256;
+    return 0;
+}
+
+struct BufView {
+    float *ptr;
+    int64_t ld;
+};
+static BufView view(const Layout &L, void *arena, int b) {
+    return BufView{reinterpret_cast<float *>(reinterpret_cast<char *>(arena) + L.buf_off[b]), L.buf_ld[b]};
+}
+
+static Gather op_gather(const POp &o, const mopa_scn_metadata *m, bool for_dinput) {
+    // forward / d_weight index by the op's OUTPUT rows; d_input by its INPUT rows
+    if (o.type == OP_SUBM) return subm_gather(m->levels[o.level_in]);
+    const bool down = o.type == OP_CONV;  // fine -> coarse
+    const Level &fine = m->levels[down ? o.level_in : o.level_out];
+    const Level &coarse = m->levels[down ? o.level_out : o.level_in];
+    const bool rows_are_coarse = down != for_dinput;
+    return rows_are_coarse ? child_gather(fine, coarse) : select_gather(fine, coarse);
+}
+
+}  // namespace mopa
+
+using namespace mopa;
+
+extern "C" {
+
+mopa_scn_program *mopa_scn_Program_new(const int32_t *ops, int n_ops, const int32_t *bufs, int n_bufs, int in_planes,
+                                       int in_buf, int out_buf, int64_t spatial_size, int n_levels, int device) {
+    auto *p = new mopa_scn_program();
+    p->in_planes = in_planes; p->in_buf = in_buf; p->out_buf = out_buf; p->spatial = spatial_size; p->n_levels = n_levels;
+    p->device = device;
+    for (int i = 0; i < n_ops; ++i) {
+        const int32_t *r = ops + (size_t)i * kOpWidth;
+        POp o;
+        o.type = r[0]; o.in = r[1]; o.out = r[2]; o.level_in = r[4]; o.level_out = r[5]; o.n_in = r[6]; o.n_out = r[7];
+        o.param = r[8];
+        memcpy(&o.leak, r + 9, 4); memcpy(&o.eps, r + 10, 4); memcpy(&o.momentum, r + 11, 4);
+        p->ops.push_back(o);
+    }
+    for (int i = 0; i < n_bufs; ++i) {
+        const int32_t *r = bufs + (size_t)i * kBufWidth;
+        p->bufs.push_back(PBuf{r[0], r[1], r[2], r[3]});
+    }
+    const size_t ws = bn_workspace_bytes(256);
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p->bn_ws, ws) != cudaSuccess ||
+        cudaMemset(p->bn_ws, 0, ws) != cudaSuccess) {
+        fail(__FILE__, __LINE__, "Program_new: cannot allocate the BatchNorm workspace on the device");
+        delete p;
+        return nullptr;
+    }
+    return p;
+}
+
+void mopa_scn_Program_delete(mopa_scn_program *p) {
+    if (!p) return;
+    if (p->bn_ws) cudaFree(p->bn_ws);
+    delete p;
+}
+
+// Voxelise + build every level / table the program uses (geometry stream), then size the arenas.
+// sizes_out: [act_bytes, grad_bytes, scratch_bytes]; n_active_out: n_levels entries.
+int mopa_scn_Program_prepare(mopa_scn_program *p, mopa_scn_metadata *m, const int64_t *coords, int64_t n, int ncols,
+                             int coords_on_device, int precision, void *stream, int64_t *n_active_out,
+                             uint64_t *sizes_out) {
+    MOPA_CHECK(p && m, "null program / metadata");
+    cudaStream_t main = (cudaStream_t)stream, gs;
+    MOPA_CUDA(cudaSetDevice(m->device));
+    MOPA_TRY(geom_stream(m->device, &gs));
+    m->last_stream = main;
+    if (coords_on_device) {  // the coordinates may have been produced on the caller's stream
+        if (!m->geom_done) MOPA_CUDA(cudaEventCreateWithFlags(&m->geom_done, cudaEventDisableTiming));
+        MOPA_CUDA(cudaEventRecord(m->geom_done, main));
+        MOPA_CUDA(cudaStreamWaitEvent(gs, m->geom_done, 0));
+    }
+    MOPA_TRY(set_locations(m, p->spatial, coords, n, ncols, coords_on_device, gs));
+    for (int l = 0; l + 1 < p->n_levels; ++l) MOPA_TRY(ensure_down(m, l, gs));
+    bool need_subm[32] = {false};
+    for (const POp &o : p->ops)
+        if (o.type == OP_SUBM) need_subm[o.level_in] = true;
+    for (int l = 0; l < p->n_levels; ++l)
+        if (need_subm[l]) MOPA_TRY(ensure_subm(m, l, gs));
+    if (!m->geom_done) MOPA_CUDA(cudaEventCreateWithFlags(&m->geom_done, cudaEventDisableTiming));
+    MOPA_CUDA(cudaEventRecord(m->geom_done, gs));
+    MOPA_CUDA(cudaStreamWaitEvent(main, m->geom_done, 0));
+    Layout L;
+    MOPA_TRY(make_layout(p, m, precision, L));
+    for (int l = 0; l < p->n_levels; ++l) n_active_out[l] = m->levels[l].V;
+    sizes_out[0] = L.act_bytes;
+    sizes_out[1] = L.grad_bytes;
+    sizes_out[2] = L.packed_bytes + L.dw_bytes;
+    return 0;
+}
+
+// params[op.param ...]: conv -> {weight}; BN -> {weight, bias, running_mean, running_var}
+int mopa_scn_Program_forward(mopa_scn_program *p, mopa_scn_metadata *m, const float *feats, int64_t ld_feats,
+                             const void *const *params, int train, int precision, void *act_arena, void *scratch,
+                             float *out, int64_t ld_out, void *stream) {
+    MOPA_CHECK(p && m && act_arena && scratch, "Program_forward: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    MOPA_CUDA(cudaSetDevice(m->device));
+    m->last_stream = s;
+    Layout L;
+    MOPA_TRY(make_layout(p, m, precision, L));
+    float *packed = reinterpret_cast<float *>(scratch);
+    BufView b0 = view(L, act_arena, p->in_buf);
+    MOPA_TRY(mopa_scn_InputLayer_updateOutput(m, feats, ld_feats, p->in_planes, b0.ptr, b0.ld, s));
+    for (size_t i = 0; i < p->ops.size(); ++i) {
+        const POp &o = p->ops[i];
+        BufView in = view(L, act_arena, o.in), ob = view(L, act_arena, o.out);
+        if (o.type == OP_BN) {
+            float *save = reinterpret_cast<float *>(reinterpret_cast<char *>(act_arena) + L.bn_off[i]);
+            MOPA_TRY(bn_forward(in.ptr, in.ld, ob.ptr, ob.ld, save, save + o.n_in, (float *)params[o.param + 2],
+                                (float *)params[o.param + 3], (const float *)params[o.param],
+                                (const float *)params[o.param + 1], o.eps, o.momentum, train, o.leak,
+                                m->levels[o.level_in].V, o.n_in, p->bn_ws, s));
+            continue;
+        }
+        const int volume = o.type == OP_SUBM ? 27 : 8;
+        const float *w = (const float *)params[o.param];
+        const float *pk = nullptr;
+        if (conv_uses_packed(o.n_in, o.n_out)) {
+            MOPA_TRY(pack_weights(w, volume, o.n_in, o.n_out, 0, 0, precision, packed, s));
+            pk = packed;
+        }
+        MOPA_TRY(conv_apply(op_gather(o, m, false), in.ptr, in.ld, ob.ptr, ob.ld, w, pk, o.n_in, o.n_out, 0, 0, precision, s));
+    }
+    BufView last = view(L, act_arena, p->out_buf);
+    return mopa_scn_OutputLayer_updateOutput(m, last.ptr, last.ld, p->bufs[p->out_buf].channels, out, ld_out, s);
+}
+
+// param_grads mirrors params (entries may be NULL: no gradient wanted). d_feats may be NULL.
+int mopa_scn_Program_backward(mopa_scn_program *p, mopa_scn_metadata *m, const void *const *params,
+                              void *const *param_grads, int train, int precision, const void *act_arena,
+                              void *grad_arena, void *scratch, const float *d_out, int64_t ld_dout, float *d_feats,
+                              int64_t ld_dfeats, void *stream) {
+    MOPA_CHECK(p && m && act_arena && grad_arena && scratch, "Program_backward: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    MOPA_CUDA(cudaSetDevice(m->device));
+    m->last_stream = s;
+    Layout L;
+    MOPA_TRY(make_layout(p, m, precision, L));
+    float *packed = reinterpret_cast<float *>(scratch);
+    void *dw_ws = reinterpret_cast<char *>(scratch) + L.packed_bytes;
+    void *act = const_cast<void *>(act_arena);
+    const size_t nb = p->bufs.size();
+    std::vector<char> written(nb, 0);
+    auto mark = [&](int b) {
+        written[b] = 1;
+        for (size_t c = 0; c < nb; ++c)
+            if (p->bufs[c].parent == b) written[c] = 1;
+    };
+    BufView g_last = view(L, grad_arena, p->out_buf);
+    MOPA_TRY(mopa_scn_OutputLayer_updateGradInput(m, g_last.ptr, g_last.ld, d_out, ld_dout, p->bufs[p->out_buf].channels, s));
+    mark(p->out_buf);
+    for (int i = (int)p->ops.size() - 1; i >= 0; --i) {
+        const POp &o = p->ops[i];
+        const int volume = o.type == OP_SUBM ? 27 : 8;
+        if (!written[o.out]) {  // output feeds nothing that reaches the loss: parameters get a zero gradient
+            const size_t n = o.type == OP_BN ? (size_t)o.n_in : (size_t)volume * o.n_in * o.n_out;
+            if (param_grads[o.param]) MOPA_CUDA(cudaMemsetAsync(param_grads[o.param], 0, n * 4, s));
+            if (o.type == OP_BN && param_grads[o.param + 1]) MOPA_CUDA(cudaMemsetAsync(param_grads[o.param + 1], 0, n * 4, s));
+            continue;
+        }
+        if (p->bufs[o.in].parent < 0) {  // overwriting a joined buffer would clobber slices that were already written
+            for (size_t c = 0; c < nb; ++c)
+                MOPA_CHECK(!(p->bufs[c].parent == o.in && written[c] && !written[o.in]),
+                           "unsupported program: a joined buffer receives its gradient after one of its slices");
+        }
+        const int accumulate = written[o.in];
+        const bool need_din = o.in != p->in_buf || d_feats != nullptr;
+        BufView x = view(L, act, o.in), dx = view(L, grad_arena, o.in), dy = view(L, grad_arena, o.out);
+        if (o.type == OP_BN) {
+            const float *save = reinterpret_cast<const float *>(reinterpret_cast<const char *>(act) + L.bn_off[i]);
+            MOPA_TRY(bn_backward(x.ptr, x.ld, need_din ? dx.ptr : nullptr, dx.ld, dy.ptr, dy.ld, save, save + o.n_in,
+                                 (const float *)params[o.param], (const float *)params[o.param + 1],
+                                 (float *)param_grads[o.param], (float *)param_grads[o.param + 1], o.leak, train,
+                                 m->levels[o.level_in].V, o.n_in, p->bn_ws, accumulate, s));
+        } else {
+            const float *w = (const float *)params[o.param];
+            if (need_din) {
+                const float *pk = nullptr;
+                if (conv_uses_packed(o.n_out, o.n_in)) {
+                    MOPA_TRY(pack_weights(w, volume, o.n_in, o.n_out, 1, o.type == OP_SUBM ? 1 : 0, precision, packed, s));
+                    pk = packed;
+                }
+                Gather g = op_gather(o, m, true);
+                g.accumulate = accumulate;
+                MOPA_TRY(conv_apply(g, dy.ptr, dy.ld, dx.ptr, dx.ld, w, pk, o.n_in, o.n_out, 1, o.type == OP_SUBM ? 1 : 0,
+                                    precision, s));
+            }
+            if (param_grads[o.param])
+                MOPA_TRY(conv_dweight(op_gather(o, m, false), x.ptr, x.ld, dy.ptr, dy.ld, (float *)param_grads[o.param],
+                                      o.n_in, o.n_out, precision, dw_ws, L.dw_bytes, s));
+        }
+        if (need_din) mark(o.in);
+    }
+    if (d_feats) {
+        BufView g0 = view(L, grad_arena, p->in_buf);
+        MOPA_CHECK(written[p->in_buf], "input gradient requested but nothing reaches the input");
+        MOPA_TRY(mopa_scn_InputLayer_updateGradInput(m, d_feats, ld_dfeats, g0.ptr, g0.ld, p->in_planes, s));
+    }
+    return 0;
+}
+
+}  // extern "C"

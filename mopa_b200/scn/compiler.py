@@ -1,0 +1,255 @@
+"""Compiles an scn.Sequential(InputLayer, ..., OutputLayer) module tree into the op list the native executor runs
+(csrc/program.cu, `mopa_scn_Program_*` in include/mopa_scn.h), and wraps it in ONE autograd Function.
+
+The module tree stays the source of truth (parameters, buffers, train/eval flags are read from it on every call); only
+the Python-level walk over ~90 modules per forward (the reference's scn.Sequential.forward, scn_unet.py:32-34) is
+replaced. Trees containing a module the executor does not know (NetworkInNetwork, AddTable, ...) are not compiled and
+run module by module instead. `MOPA_SCN_EAGER=1` forces the module-by-module path.
+"""
+import ctypes
+import os
+import struct
+import weakref
+
+import numpy as np
+import torch
+from torch.autograd import Function
+
+from .. import _lib
+from . import functional as F
+from . import modules as M
+
+OP_SUBM, OP_CONV, OP_DECONV, OP_BN = 1, 2, 3, 4
+
+
+class _Unsupported(Exception):
+    pass
+
+
+def _fbits(x):
+    return struct.unpack("i", struct.pack("f", float(x)))[0]
+
+
+class CompiledProgram:
+    def __init__(self, root):
+        mods = list(root._modules.values())
+        if len(mods) < 2 or not isinstance(mods[0], M.InputLayer) or not isinstance(mods[-1], M.OutputLayer):
+            raise _Unsupported("not an InputLayer ... OutputLayer chain")
+        inp = mods[0]
+        if inp.mode != 4 or inp.dimension != 3:
+            raise _Unsupported("InputLayer mode/dimension")
+        self.spatial = M._cube(inp.spatial_size)
+        self.ops, self.bufs, self.slots = [], [], []  # slots: (module, attribute name) per param pointer slot
+        self.max_level = 0
+        self.in_planes = None
+        b = self._new_buf(0, None)  # channels filled in by the first consumer
+        for mod in mods[1:-1]:
+            b = self._walk(mod, b)
+        if isinstance(b, list):
+            raise _Unsupported("chain ends in a table")
+        if self.bufs[b][1] is None:
+            raise _Unsupported("no layer between InputLayer and OutputLayer")
+        self.out_buf = b
+        self.in_planes = self.bufs[0][1]
+        self.n_levels = self.max_level + 1
+        self.bn_modules = [m for m, a in self.slots if a == "running_mean"]
+        self.handle = None
+        self._lib = _lib.load()
+
+    # -- tree walk --------------------------------------------------------------------------------------------------
+    def _new_buf(self, level, channels):
+        self.bufs.append([level, channels, -1, 0])
+        self.max_level = max(self.max_level, level)
+        return len(self.bufs) - 1
+
+    def _channels(self, b, expected):
+        if self.bufs[b][1] is None:
+            self.bufs[b][1] = expected
+        if self.bufs[b][1] != expected:
+            raise _Unsupported("plane count mismatch")
+
+    def _walk(self, mod, b):
+        if isinstance(mod, M.ConcatTable):
+            return [self._walk(c, b) for c in mod._modules.values()]
+        if isinstance(mod, (M.Sequential, torch.nn.Sequential)):
+            for c in mod._modules.values():
+                b = self._walk(c, b)
+            return b
+        if isinstance(mod, M.Identity):
+            return b
+        if isinstance(mod, M.JoinTable):
+            if not isinstance(b, list) or any(isinstance(x, list) for x in b):
+                raise _Unsupported("JoinTable input")
+            level = self.bufs[b[0]][0]
+            total = 0
+            for x in b:
+                if self.bufs[x][2] != -1 or x == 0 or self.bufs[x][0] != level or self.bufs[x][1] is None or x in b[:b.index(x)]:
+                    raise _Unsupported("JoinTable of a shared / already joined buffer")
+                total += self.bufs[x][1]
+            j = self._new_buf(level, total)
+            off = 0
+            for x in b:
+                self.bufs[x][2], self.bufs[x][3] = j, off
+                off += self.bufs[x][1]
+            return j
+        if isinstance(b, list):
+            raise _Unsupported("table fed to a non-table module")
+        level = self.bufs[b][0]
+        if isinstance(mod, M.BatchNormalization):
+            self._channels(b, mod.nPlanes)
+            out = self._new_buf(level, mod.nPlanes)
+            self._op(OP_BN, b, out, level, level, mod.nPlanes, mod.nPlanes, mod.leakiness, mod.eps, mod.momentum)
+            self.slots += [(mod, "weight"), (mod, "bias"), (mod, "running_mean"), (mod, "running_var")]
+            return out
+        if isinstance(mod, M.SubmanifoldConvolution):
+            self._channels(b, mod.nIn)
+            out = self._new_buf(level, mod.nOut)
+            self._op(OP_SUBM, b, out, level, level, mod.nIn, mod.nOut)
+            self.slots.append((mod, "weight"))
+            return out
+        if isinstance(mod, M.Convolution):
+            self._channels(b, mod.nIn)
+            out = self._new_buf(level + 1, mod.nOut)
+            self._op(OP_CONV, b, out, level, level + 1, mod.nIn, mod.nOut)
+            self.slots.append((mod, "weight"))
+            return out
+        if isinstance(mod, M.Deconvolution):
+            if level == 0:
+                raise _Unsupported("Deconvolution above the input level")
+            self._channels(b, mod.nIn)
+            out = self._new_buf(level - 1, mod.nOut)
+            self._op(OP_DECONV, b, out, level, level - 1, mod.nIn, mod.nOut)
+            self.slots.append((mod, "weight"))
+            return out
+        raise _Unsupported(type(mod).__name__)
+
+    def _op(self, kind, b_in, b_out, l_in, l_out, n_in, n_out, leak=0.0, eps=0.0, momentum=0.0):
+        self.ops.append([kind, b_in, b_out, 0, l_in, l_out, n_in, n_out, len(self.slots), _fbits(leak), _fbits(eps),
+                         _fbits(momentum)])
+
+    # -- runtime ----------------------------------------------------------------------------------------------------
+    def ensure_handle(self, device_index):
+        if self.handle is None:
+            if self.spatial % (1 << self.max_level):
+                raise _lib.ScnError("spatial size %d is not divisible by 2^%d" % (self.spatial, self.max_level))
+            ops = np.ascontiguousarray(np.array(self.ops, dtype=np.int32))
+            bufs = np.ascontiguousarray(np.array(self.bufs, dtype=np.int32))
+            h = self._lib.mopa_scn_Program_new(ops.ctypes.data, len(self.ops), bufs.ctypes.data, len(self.bufs),
+                                               self.in_planes, 0, self.out_buf, self.spatial, self.n_levels, device_index)
+            if not h:
+                raise _lib.ScnError(self._lib.mopa_scn_last_error().decode())
+            self.handle, self.device_index = h, device_index
+        elif self.device_index != device_index:
+            raise _Unsupported("module moved to another device")
+        return self.handle
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self._lib.mopa_scn_Program_delete(h)
+
+    def tensors(self):
+        return [getattr(m, a) for m, a in self.slots]
+
+
+_programs = weakref.WeakKeyDictionary()
+
+
+def compiled_for(root):
+    """CompiledProgram for this module tree, or None if it cannot / should not be compiled."""
+    if os.environ.get("MOPA_SCN_EAGER") == "1":
+        return None
+    sig = tuple(id(m) for m in root.modules())
+    entry = _programs.get(root)
+    if entry is None or entry[0] != sig:
+        try:
+            entry = (sig, CompiledProgram(root))
+        except _Unsupported:
+            entry = (sig, None)
+        _programs[root] = entry
+    prog = entry[1]
+    if prog is None:
+        return None
+    if any(m.training != root.training for m in prog.bn_modules):
+        return None  # mixed train/eval BatchNorms: run module by module
+    return prog
+
+
+class _ProgramFunction(Function):
+    @staticmethod
+    def forward(ctx, prog, coords, train, feats, *trainable):
+        F._require_cuda(feats, "InputLayer features")
+        L = prog._lib
+        dev = feats.device
+        handle = prog.ensure_handle(dev.index if dev.index is not None else torch.cuda.current_device())
+        meta = F.Metadata(3, dev)
+        if coords.dtype != torch.int64:
+            coords = coords.long()
+        coords = coords.contiguous()
+        n, ncols = coords.shape
+        feats, ld = F._rows(feats)
+        if feats.shape[1] != prog.in_planes:
+            raise _lib.ScnError("expected %d input planes, got %d" % (prog.in_planes, feats.shape[1]))
+        if feats.shape[0] < n:
+            raise _lib.ScnError("fewer feature rows than coordinates")
+        prec = F._cfg["precision"]
+        stream = F._stream()
+        n_active = (ctypes.c_int64 * prog.n_levels)()
+        sizes = (ctypes.c_uint64 * 3)()
+        with torch.cuda.device(dev):
+            _lib.check(L.mopa_scn_Program_prepare(handle, meta._h, coords.data_ptr(), n, ncols, 1 if coords.is_cuda else 0,
+                                                  prec, stream, n_active, sizes))
+            meta.n_points = n
+            act = torch.empty(sizes[0], dtype=torch.uint8, device=dev)
+            scratch = torch.empty(sizes[2], dtype=torch.uint8, device=dev)
+            out = torch.empty(n, prog.bufs[prog.out_buf][1], dtype=torch.float32, device=dev)
+            tensors = prog.tensors()
+            params = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+            _lib.check(L.mopa_scn_Program_forward(handle, meta._h, feats.data_ptr(), ld, params, 1 if train else 0, prec,
+                                                  act.data_ptr(), scratch.data_ptr(), out.data_ptr(), out.shape[1], stream))
+        ctx.prog, ctx.meta, ctx.act, ctx.train, ctx.prec = prog, meta, act, train, prec
+        ctx.sizes = (int(sizes[1]), int(sizes[2]))
+        ctx.n_rows = feats.shape[0]
+        ctx.tensors = tensors  # the exact tensors the forward used (EMA swaps replace .data, not the tensor objects)
+        ctx.last_metadata = meta
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        prog, meta, L = ctx.prog, ctx.meta, ctx.prog._lib
+        d_out, ld_dout = F._rows(d_out)
+        dev = d_out.device
+        tensors = ctx.tensors
+        need = ctx.needs_input_grad  # (prog, coords, train, feats, *trainable)
+        trainable_idx = [i for i, (m, a) in enumerate(prog.slots) if not a.startswith("running_")]
+        sizes = [tensors[i].numel() for i in trainable_idx]
+        with torch.cuda.device(dev):
+            flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            grads, ptrs, off = [], [None] * len(tensors), 0
+            for j, (i, sz) in enumerate(zip(trainable_idx, sizes)):
+                if need[4 + j]:
+                    g = flat[off:off + sz].view_as(tensors[i])
+                    ptrs[i] = g.data_ptr()
+                    grads.append(g)
+                else:
+                    grads.append(None)
+                off += sz
+            params = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+            pgrads = (ctypes.c_void_p * len(tensors))(*ptrs)
+            grad_arena = torch.empty(ctx.sizes[0], dtype=torch.uint8, device=dev)
+            scratch = torch.empty(ctx.sizes[1], dtype=torch.uint8, device=dev)
+            d_feats = torch.zeros(ctx.n_rows, prog.in_planes, dtype=torch.float32, device=dev) if need[3] else None
+            _lib.check(L.mopa_scn_Program_backward(
+                prog.handle, meta._h, params, pgrads, 1 if ctx.train else 0, ctx.prec, ctx.act.data_ptr(),
+                grad_arena.data_ptr(), scratch.data_ptr(), d_out.data_ptr(), ld_dout,
+                d_feats.data_ptr() if d_feats is not None else None, prog.in_planes, F._stream()))
+        return (None, None, None, d_feats) + tuple(grads)
+
+
+def run(prog, root, input):
+    coords, feats = input[0], input[1]
+    if coords.dim() != 2 or coords.shape[1] not in (3, 4):
+        raise _lib.ScnError("InputLayer: coords must be (N, 3) or (N, 4)")
+    tensors = prog.tensors()
+    trainable = [t for t, (m, a) in zip(tensors, prog.slots) if not a.startswith("running_")]
+    return _ProgramFunction.apply(prog, coords, root.training, feats, *trainable)

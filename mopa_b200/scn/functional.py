@@ -149,7 +149,7 @@ def _bn_workspace(device):
     """Persistent zero-initialised scratch per device (the library leaves it zeroed after every call)."""
     ws = _bn_ws.get(device)
     if ws is None:
-        nbytes = _lib.load().mopa_scn_bnWorkspaceBytes(1024)
+        nbytes = _lib.load().mopa_scn_bnWorkspaceBytes(256)
         ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         _bn_ws[device] = ws
     return ws

@@ -58,6 +58,19 @@ class Sequential(nn.Sequential):
         self._modules[str(len(self._modules))] = module
         return self
 
+    def forward(self, input):
+        # [coords, feats] entering an InputLayer ... OutputLayer chain: run the compiled program (one native call for
+        # the whole forward, one for the backward) when every module is known to the executor; else module by module.
+        if isinstance(input, (list, tuple)) and len(self._modules) >= 2 and isinstance(self._modules["0"], InputLayer) \
+                and torch.is_tensor(input[1]) and input[1].is_cuda:
+            from . import compiler
+            prog = compiler.compiled_for(self)
+            if prog is not None:
+                return compiler.run(prog, self, input)
+        for module in self._modules.values():
+            input = module(input)
+        return input
+
     def input_spatial_size(self, out_size):
         for m in reversed(self._modules.values()):
             out_size = m.input_spatial_size(out_size)

@@ -223,9 +223,12 @@ def _rel_l2_cos(a, b):
 GRAD_NET = {"fp32": (6e-2, 0.999), "tf32": (0.2, 0.98)}
 
 
+@pytest.mark.parametrize("mode", ["compiled", "eager"])
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
-def test_unet_scn_forward_backward_matches_oracle(scn, precision):
+def test_unet_scn_forward_backward_matches_oracle(scn, precision, mode, monkeypatch):
+    """mode: the native whole-network executor (default) or the module-by-module path (MOPA_SCN_EAGER=1)."""
     from mopa_b200.unet_scn import UNetSCN
+    monkeypatch.setenv("MOPA_SCN_EAGER", "1" if mode == "eager" else "0")
     scn.set_precision(precision)
     tol = TOL_NET[precision]
     coords, feats = small_batch(2, 250, 2)
@@ -248,6 +251,42 @@ def test_unet_scn_forward_backward_matches_oracle(scn, precision):
     assert rel_err(net.sparseModel[3].weight.grad, oracle.params["sparseModel.3.weight"].grad) < tol
     for name, buf in net.named_buffers():  # running statistics of all 26 BatchNorms
         assert rel_err(buf, oracle.params[name]) < tol, name
+
+
+def test_compiled_and_eager_paths_agree_bitwise(scn, monkeypatch):
+    """Both host paths launch the same kernels in the same order on the same layouts: outputs and grads are identical."""
+    from mopa_b200.unet_scn import UNetSCN
+    from mopa_b200.scn import compiler
+    scn.set_precision("tf32")
+    coords, feats = small_batch(2, 200, 9)
+    net = UNetSCN(1).cuda()
+    assert compiler.compiled_for(net.sparseModel) is not None
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MOPA_SCN_EAGER", mode)
+        net.zero_grad(set_to_none=True)
+        f = torch.from_numpy(feats).cuda().requires_grad_(True)
+        out = net([torch.from_numpy(coords), f])
+        out.square().sum().backward()
+        res[mode] = (out.detach().clone(), [p.grad.clone() for p in net.parameters()], f.grad.clone())
+    assert torch.equal(res["0"][0], res["1"][0])
+    assert torch.equal(res["0"][2], res["1"][2])
+    for a, b in zip(res["0"][1], res["1"][1]):
+        assert torch.equal(a, b)
+
+
+def test_compiled_path_handles_device_coords_surplus_rows_and_no_grad(scn):
+    from mopa_b200.unet_scn import UNetSCN
+    coords, feats = small_batch(2, 150, 10)
+    feats = np.concatenate([feats, np.ones((7, 1), np.float32)], 0)  # surplus feature rows (nuscenes_dataloader.py:426)
+    net = UNetSCN(1).cuda()
+    a = net([torch.from_numpy(coords), torch.from_numpy(feats).cuda()])
+    b = net([torch.from_numpy(coords).cuda(), torch.from_numpy(feats).cuda()])
+    assert a.shape == (coords.shape[0], 16) and torch.equal(a, b)
+    net.eval()
+    with torch.no_grad():
+        c = net([torch.from_numpy(coords), torch.from_numpy(feats).cuda()])
+    assert c.shape == a.shape and not c.requires_grad
 
 
 def test_unet_eval_mode_and_batch_separation(scn):
