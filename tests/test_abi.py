@@ -1,0 +1,95 @@
+"""CPU-side checks of the C-ABI boundary: libmopa_scn.so loads without a GPU, exports every symbol include/mopa_scn.h
+declares, and the ctypes prototypes in mopa_b200/_lib.py agree with the header's argument lists. No compute calls."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from mopa_b200 import _build, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mopa_scn.h")
+
+
+def _declarations():
+    """name -> list of parameter strings, parsed from the header (comments stripped)."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", " ", src)
+    src = re.sub(r"^\s*#.*$", " ", src, flags=re.M)
+    decls = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(mopa_scn_\w+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
+        name, args = m.group(2), " ".join(m.group(3).split())
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        decls[name] = (" ".join(m.group(1).split()), params)
+    return decls
+
+
+def _ctype_of(param):
+    p = param.replace("const ", "").strip()
+    if "*" in p:
+        return "ptr"
+    base = p.rsplit(" ", 1)[0].strip() if " " in p else p
+    return {"int": "int", "int64_t": "i64", "float": "float", "size_t": "size", "uint64_t": "u64"}[base]
+
+
+_CT = {ctypes.c_int: "int", ctypes.c_int64: "i64", ctypes.c_float: "float", ctypes.c_size_t: "size",
+       ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr"}
+
+
+def _kind(ct):
+    if ct in _CT:
+        return _CT[ct]
+    if isinstance(ct, type) and issubclass(ct, ctypes._Pointer):
+        return "ptr"
+    raise AssertionError("unmapped ctypes type %r" % (ct,))
+
+
+def test_header_declares_what_python_binds():
+    decls = _declarations()
+    assert set(decls) == set(_lib.PROTOTYPES), (set(decls) ^ set(_lib.PROTOTYPES))
+
+
+@pytest.mark.parametrize("name", sorted(_lib.PROTOTYPES))
+def test_prototype_matches_header(name):
+    ret, params = _declarations()[name]
+    _, argtypes = _lib.PROTOTYPES[name]
+    assert len(params) == len(argtypes), (name, params)
+    for p, ct in zip(params, argtypes):
+        want, got = _ctype_of(p), _kind(ct)
+        if want == "size" and got == "size":
+            continue
+        assert want == got, (name, p, ct)
+
+
+def test_library_builds_loads_and_exports_every_symbol():
+    path = _build.build()  # no-op when the in-tree .so is fresh
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)  # must load on a box without a GPU / driver (cudart is linked statically)
+    for name in _declarations():
+        assert hasattr(lib, name), "libmopa_scn.so does not export %s" % name
+    lib.mopa_scn_abi_version.restype = ctypes.c_int
+    assert lib.mopa_scn_abi_version() == 1
+
+
+def test_metadata_new_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = _lib.load()
+    assert not lib.mopa_scn_Metadata_new(3, 0)
+    assert b"no CPU path" in lib.mopa_scn_last_error() or b"cuda" in lib.mopa_scn_last_error().lower()
+    import mopa_b200.scn as scn
+    with pytest.raises(_lib.ScnError):
+        scn.InputLayer(3, 4096, mode=4)([torch.zeros(4, 4, dtype=torch.long), torch.ones(4, 1)])
+
+
+def test_no_product_import_of_oracle():
+    """The product package must never import the oracle (a CPU fallback would void parity claims)."""
+    pkg = os.path.join(ROOT, "mopa_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
