@@ -157,49 +157,55 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def conv_fwd_bytes(rec, rules):
-    """fwd B = R(4 Cin + 8) + 4 Vout Cout + 4 K Cin Cout."""
-    return rules * (4 * rec["n_in"] + 8) + 4 * rec["rows_out"] * rec["n_out"] + 4 * rec["volume"] * rec["n_in"] * rec["n_out"]
+def op_bytes_flops(rec):
+    """Algorithmic bytes / flops of one recorded op, SURVEY.md 8(d) (fp32 features, int32 rule pairs)."""
+    cls = rec["tag"] // 10
+    r, ci, co, k = rec["rules"], rec["c_in"], rec["c_out"], rec["volume"]
+    if cls in (1, 2):  # gather conv (forward; d_input = same kernel, roles swapped): R(4 Cin + 8) + 4 Vout Cout + 4 K Cin Cout
+        return r * (4 * ci + 8) + 4 * rec["rows_out"] * co + 4 * k * ci * co, 2.0 * r * ci * co
+    if cls == 3:  # d_weight: R(4 (Cin + Cout) + 8) + 4 K Cin Cout
+        return r * (4 * (ci + co) + 8) + 4 * k * ci * co, 2.0 * r * ci * co
+    if cls == 4:  # BatchNorm+ReLU forward (train): 3 * 4 V C
+        return 3 * 4 * rec["rows_out"] * ci, 0.0
+    if cls == 5:  # backward: 5 * 4 V C
+        return 5 * 4 * rec["rows_out"] * ci, 0.0
+    return 0, 0.0
 
 
 def roofline_pass(net, batches_dev, steps, peaks):
-    """Times every conv-forward launch of the gather-MMA kernel with CUDA events on the launching stream."""
-    import mopa_b200.scn.functional as F
-    F.profile_log = []
+    """Per-launch device times from the library's own event log (CUDA events recorded on the launching stream around
+    each op's kernels, include/mopa_scn.h mopa_scn_Profile_*). Dominant kernel: k_gather_mma, the gather -> MMA ->
+    accumulate kernel every submanifold / strided convolution runs in forward and in the input-gradient pass."""
+    from mopa_b200 import _lib
+    _lib.profile_enable(True)
     for i in range(steps):
         c, f = batches_dev[i % len(batches_dev)]
         out = net([c, f])
         out.sum().backward()
-    torch.cuda.synchronize()
-    log, F.profile_log = F.profile_log, None
-    rule_cache = {}
-    tot = {"subm": [0.0, 0.0, 0, 0.0], "all": [0.0, 0.0, 0, 0.0]}
-    for rec in log:
-        ms = rec["ev"][0].elapsed_time(rec["ev"][1])
-        if rec["kind"] == "subm":
-            key = (id(rec["metadata"]), rec["size"])
-            if key not in rule_cache:
-                rule_cache[key] = sum(rec["metadata"].submanifold_rule_counts(rec["size"]))
-            rules = rule_cache[key]
-        else:
-            rules = max(rec["rows_in"], rec["rows_out"])  # one rule per fine site
-        b = conv_fwd_bytes(rec, rules)
-        fl = 2.0 * rules * rec["n_in"] * rec["n_out"]
-        for k in ("all",) + (("subm",) if rec["kind"] == "subm" else ()):
-            tot[k][0] += b
-            tot[k][1] += ms * 1e-3
-            tot[k][2] += 1
-            tot[k][3] += fl
-    b, t, n, fl = tot["subm"]
+    recs = _lib.profile_read()
+    _lib.profile_enable(False)
+    names = {1: "conv_forward", 2: "conv_d_input", 3: "conv_d_weight", 4: "bn_forward", 5: "bn_backward"}
+    cls = {}
+    for r in recs:
+        c = r["tag"] // 10
+        if c not in names or (c <= 2 and r["c_in"] < 16):
+            continue  # the 1 -> 16 input conv runs a small SIMT kernel, not k_gather_mma
+        b, fl = op_bytes_flops(r)
+        e = cls.setdefault(names[c], [0.0, 0.0, 0, 0.0])
+        e[0] += b; e[1] += r["ms"] * 1e-3; e[2] += 1; e[3] += fl
     peak = peaks.get("hbm_gbs", 6650.0)
+    b = sum(cls[k][0] for k in ("conv_forward", "conv_d_input") if k in cls)
+    t = sum(cls[k][1] for k in ("conv_forward", "conv_d_input") if k in cls)
+    n = sum(cls[k][2] for k in ("conv_forward", "conv_d_input") if k in cls)
+    fl = sum(cls[k][3] for k in ("conv_forward", "conv_d_input") if k in cls)
     ach = b / t / 1e9 if t > 0 else 0.0
-    return {"bound": "hbm", "kernel": "k_gather_mma (submanifold conv forward, 14 launches/step)", "achieved": ach, "peak": peak,
-            "unit": "GB/s", "frac": ach / peak, "traffic": None,
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (sustained copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+    return {"bound": "hbm", "kernel": "k_gather_mma (gather -> TF32 MMA -> accumulate; conv forward + d_input, %d launches/step)" % (n // max(steps, 1)),
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
             "launches_timed": n, "avg_launch_us": 1e6 * t / max(n, 1), "algorithmic_bytes_per_launch": b / max(n, 1),
             "tflops_useful": fl / t / 1e12 if t > 0 else 0.0,
-            "all_conv_forward": {"achieved": tot["all"][0] / tot["all"][1] / 1e9 if tot["all"][1] else 0.0,
-                                 "launches": tot["all"][2]}}
+            "per_class": {k: {"ms_per_step": 1e3 * v[1] / max(steps, 1), "gbs": v[0] / v[1] / 1e9 if v[1] else 0.0,
+                              "frac": v[0] / v[1] / 1e9 / peak if v[1] else 0.0, "launches": v[2]} for k, v in cls.items()}}
 
 
 def run_ours(a):

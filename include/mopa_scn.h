@@ -181,6 +181,21 @@ int mopa_scn_Program_backward(mopa_scn_program *p, mopa_scn_metadata *m, const v
 /* ---- instrumentation: number of kernels this library has launched in this process (bench.py `gpu_launches`) --- */
 int64_t mopa_scn_kernelLaunchCount(void);
 
+/* Per-kernel timing for bench.py's roofline leg (no reference counterpart). While enabled, every conv / BatchNorm /
+ * IO-layer op brackets its kernels with CUDA events ON THE LAUNCHING STREAM and records its shape. tag = 10 * class + op:
+ * class 1 conv forward, 2 conv d_input, 3 conv d_weight, 4 BatchNorm forward, 5 BatchNorm backward, 6 IO layers;
+ * op 1 submanifold, 2 convolution, 3 deconvolution, 0 n/a. `rules` is the exact rule count of the op's rulebook.
+ * _enable(on) clears the log; _read synchronises the device. Off by default; costs nothing when off. */
+typedef struct mopa_scn_profile_record {
+    int32_t tag, volume, c_in, c_out;
+    int64_t rows_out, rows_in, rules;
+    float ms;
+    int32_t reserved;
+} mopa_scn_profile_record;
+int mopa_scn_Profile_enable(int on);
+int64_t mopa_scn_Profile_count(void);
+int mopa_scn_Profile_read(mopa_scn_profile_record *records, int64_t max_records);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,7 +57,16 @@ PROTOTYPES = {
     "mopa_scn_Program_forward": (_int, [_p, _p, _p, _i64, _p, _int, _int, _p, _p, _p, _i64, _p]),
     "mopa_scn_Program_backward": (_int, [_p, _p, _p, _p, _int, _int, _p, _p, _p, _p, _i64, _p, _i64, _p]),
     "mopa_scn_kernelLaunchCount": (_i64, []),
+    "mopa_scn_Profile_enable": (_int, [_int]),
+    "mopa_scn_Profile_count": (_i64, []),
+    "mopa_scn_Profile_read": (_int, [_p, _i64]),
 }
+
+
+class ProfileRecord(ctypes.Structure):
+    """mopa_scn_profile_record (include/mopa_scn.h)"""
+    _fields_ = [("tag", _c.c_int32), ("volume", _c.c_int32), ("c_in", _c.c_int32), ("c_out", _c.c_int32),
+                ("rows_out", _i64), ("rows_in", _i64), ("rules", _i64), ("ms", _f), ("reserved", _c.c_int32)]
 
 _lib = None
 
@@ -100,3 +109,16 @@ def check(status):
 
 def kernel_launches():
     return int(load().mopa_scn_kernelLaunchCount())
+
+
+def profile_enable(on):
+    check(load().mopa_scn_Profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """List of dicts, one per op launched since profile_enable(True) (synchronises the device)."""
+    lib = load()
+    n = int(lib.mopa_scn_Profile_count())
+    recs = (ProfileRecord * max(n, 1))()
+    check(lib.mopa_scn_Profile_read(ctypes.cast(recs, _p), n))
+    return [{f: getattr(recs[i], f) for f, _ in ProfileRecord._fields_ if f != "reserved"} for i in range(n)]

@@ -10,8 +10,11 @@ namespace mopa {
 
 // ------------------------------------------------------------------------------------------------ BatchNorm
 constexpr int kBnMaxBlocks = 4 * kNumSMs;
-// workspace layout (floats): [0] block counter (int), [8 .. 8+2C) fused scale/shift or gradMean/k, then partials
-__host__ __device__ inline size_t bn_ws_floats(int planes) { return 8 + 2 * (size_t)planes + (size_t)kBnMaxBlocks * 2 * planes; }
+constexpr int kBnMaxPlanes = 256;
+// workspace layout (floats): [0] block counter (int), [8 .. 8+2C) gradMean / k of the backward pass,
+// [8 + 512 ...) 2C fp64 accumulators (8-byte aligned). Zero between calls.
+__host__ __device__ inline size_t bn_ws_floats(int) { return 8 + 2 * (size_t)kBnMaxPlanes + 2 * 2 * (size_t)kBnMaxPlanes; }
+__device__ __forceinline__ double *bn_ws_acc(float *ws) { return reinterpret_cast<double *>(ws + 8 + 2 * kBnMaxPlanes); }
 
 template <int VEC>
 struct Vec;
@@ -97,14 +100,15 @@ __global__ void __launch_bounds__(256) k_bn_stats(const float *__restrict__ x, i
         sred[threadIdx.y * 2 * planes + planes + c0 + e] = s2[e];
     }
     __syncthreads();
-    float *partial = ws + 8 + 2 * planes;
+    // ---- block partial -> fp64 atomics on 2C global accumulators (a double sum is order-insensitive far below fp32
+    //      resolution); the last block to finish finalises and leaves the workspace zeroed for the next call
+    double *acc = bn_ws_acc(ws);
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
     for (int i = tid; i < 2 * planes; i += nthr) {
         float s = 0.f;
         for (int y = 0; y < (int)blockDim.y; ++y) s += sred[y * 2 * planes + i];
-        partial[(int64_t)blockIdx.x * 2 * planes + i] = s;
+        atomicAdd(acc + i, (double)s);
     }
-    // ---- last block to finish combines the partials in block order
     __shared__ int is_last;
     __threadfence();
     __syncthreads();
@@ -112,36 +116,15 @@ __global__ void __launch_bounds__(256) k_bn_stats(const float *__restrict__ x, i
         int *counter = reinterpret_cast<int *>(ws);
         const int done = atomicAdd(counter, 1);
         is_last = done == (int)gridDim.x - 1;
-        if (is_last) *counter = 0;  // leave the workspace zeroed for the next call
+        if (is_last) *counter = 0;
     }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // column sums of the partials: J threads per column, 4 independent accumulators each, then a shared-memory combine
-    __shared__ double sfin[512];
-    const int cols = 2 * planes;
-    int J = nthr / cols;
-    J = J < 1 ? 1 : (J > 8 ? 8 : J);
-    for (int e = tid; e < J * cols; e += nthr) {
-        const int j = e / cols, col = e - j * cols;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int blk = j;
-        for (; blk + 3 * J < (int)gridDim.x; blk += 4 * J) {
-            a0 += (double)__ldcg(partial + (int64_t)blk * cols + col);
-            a1 += (double)__ldcg(partial + (int64_t)(blk + J) * cols + col);
-            a2 += (double)__ldcg(partial + (int64_t)(blk + 2 * J) * cols + col);
-            a3 += (double)__ldcg(partial + (int64_t)(blk + 3 * J) * cols + col);
-        }
-        for (; blk < (int)gridDim.x; blk += J) a0 += (double)__ldcg(partial + (int64_t)blk * cols + col);
-        sfin[e] = (a0 + a1) + (a2 + a3);
-    }
-    __syncthreads();
     for (int c = tid; c < planes; c += nthr) {
-        double a = 0.0, b = 0.0;
-        for (int j = 0; j < J; ++j) {
-            a += sfin[j * cols + c];
-            b += sfin[j * cols + planes + c];
-        }
+        const double a = __ldcg(acc + c), b = __ldcg(acc + planes + c);
+        acc[c] = 0.0;
+        acc[planes + c] = 0.0;
         const double dn = (double)n;
         if (!BWD) {
             const double shift = (double)x[c];
@@ -326,6 +309,7 @@ int bn_forward(const float *in, int64_t ld_in, float *out, int64_t ld_out, float
     BnShape sh = bn_shape(n_active, planes, vec_ok);
     MOPA_CHECK(sh.block.x * sh.block.y <= 256, "BatchNormalization: unaligned features with more than 256 planes");
     float *ws = reinterpret_cast<float *>(workspace);
+    const int prof = prof_begin(40, nullptr, planes, planes, n_active, s);
     if (train) {
         if (sh.vec == 4)
             k_bn_stats<4, false><<<sh.grid, sh.block, sh.smem, s>>>(in, ld_in, nullptr, 0, n_active, planes, ws, nullptr,
@@ -348,6 +332,7 @@ int bn_forward(const float *in, int64_t ld_in, float *out, int64_t ld_out, float
     else
         k_bn_apply<1><<<sh.grid, sh.block, 0, s>>>(in, ld_in, out, ld_out, n_active, planes, save_mean, save_invstd, weight,
                                                    bias, leakiness);
+    prof_end(prof, s);
     MOPA_LAUNCHED();
     return 0;
 }
@@ -366,6 +351,7 @@ int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, con
     BnShape sh = bn_shape(n_active, planes, vec_ok);
     MOPA_CHECK(sh.block.x * sh.block.y <= 256, "BatchNormalization: unaligned features with more than 256 planes");
     float *ws = reinterpret_cast<float *>(workspace);
+    const int prof = prof_begin(50, nullptr, planes, planes, n_active, s);
     if (sh.vec == 4)
         k_bn_stats<4, true><<<sh.grid, sh.block, sh.smem, s>>>(in, ld_in, d_out, ld_dout, n_active, planes, ws, save_mean,
                                                                save_invstd, weight, bias, leakiness, train, 0.f, 0.f,
@@ -384,6 +370,7 @@ int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, con
                                                            save_mean, save_invstd, weight, bias, ws, leakiness, accumulate);
         MOPA_LAUNCHED();
     }
+    prof_end(prof, s);
     return 0;
 }
 

@@ -44,6 +44,13 @@ inline int fail(const char *file, int line, const std::string &msg) {
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- optional per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream around the main kernel
+// of each op; off by default and free when off. tag = 10 * class + op, class 1 conv forward, 2 conv d_input,
+// 3 conv d_weight, 4 BatchNorm forward, 5 BatchNorm backward, 6 input/output layer; op 1 subm, 2 conv, 3 deconv, 0 n/a.
+struct Gather;
+int prof_begin(int tag, const Gather *gt, int c_in, int c_out, int64_t rows, cudaStream_t s);  // -1 when profiling is off
+void prof_end(int idx, cudaStream_t s);
+
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

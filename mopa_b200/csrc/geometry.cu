@@ -21,6 +21,55 @@ namespace mopa {
 thread_local std::string g_last_error;
 std::atomic<long long> g_launches{0};
 
+// ------------------------------------------------------------------------------------------------ profiling
+struct ProfRec {
+    int tag, volume, c_in, c_out;
+    int64_t rows_out, rows_in, rules;
+    int count_slot;  // index into g_prof_counts when the rule count is computed on the device, else -1
+    cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static unsigned long long *g_prof_counts = nullptr;  // device, kProfSlots entries
+constexpr int kProfSlots = 1 << 14;
+
+__global__ void __launch_bounds__(256) k_count_valid(const int32_t *__restrict__ table, int64_t ld, int64_t V, int K,
+                                                     unsigned long long *__restrict__ out) {
+    unsigned long long c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V * K; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = i / V, o = i - k * V;
+        c += table[k * ld + o] >= 0;
+    }
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+int prof_begin(int tag, const Gather *gt, int c_in, int c_out, int64_t rows, cudaStream_t s) {
+    if (!g_prof_on) return -1;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_on || (int)g_prof.size() >= kProfSlots) return -1;
+    ProfRec r{};
+    r.tag = tag; r.c_in = c_in; r.c_out = c_out; r.rows_out = rows; r.rows_in = rows; r.rules = rows; r.count_slot = -1;
+    if (gt) {
+        r.volume = gt->volume; r.rows_out = gt->n_out; r.rows_in = gt->n_in;
+        r.rules = gt->table && gt->volume == 8 ? gt->n_in : gt->n_out;  // strided: one rule per fine site
+        if (gt->table && gt->volume == 27 && gt->n_out > 0 && g_prof_counts) {  // submanifold: count the table's rules
+            r.count_slot = (int)g_prof.size();
+            k_count_valid<<<kNumSMs * 4, 256, 0, s>>>(gt->table, gt->ld, gt->n_out, 27, g_prof_counts + r.count_slot);
+        }
+    }
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
+    cudaEventRecord(r.e0, s);
+    g_prof.push_back(r);
+    return (int)g_prof.size() - 1;
+}
+void prof_end(int idx, cudaStream_t s) {
+    if (idx < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (idx < (int)g_prof.size()) cudaEventRecord(g_prof[idx].e1, s);
+}
+
 // ------------------------------------------------------------------------------------------------ allocation
 int meta_alloc(mopa_scn_metadata *m, void **p, size_t bytes, cudaStream_t s) {
     if (bytes == 0) bytes = 16;
@@ -512,6 +561,42 @@ extern "C" {
 int mopa_scn_abi_version(void) { return MOPA_SCN_ABI_VERSION; }
 const char *mopa_scn_last_error(void) { return g_last_error.c_str(); }
 int64_t mopa_scn_kernelLaunchCount(void) { return (int64_t)g_launches.load(); }
+
+int mopa_scn_Profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (ProfRec &r : g_prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    if (on) {
+        if (!g_prof_counts) MOPA_CUDA(cudaMalloc((void **)&g_prof_counts, (size_t)kProfSlots * 8));
+        MOPA_CUDA(cudaMemset(g_prof_counts, 0, (size_t)kProfSlots * 8));
+    }
+    g_prof_on = on != 0;
+    return 0;
+}
+int64_t mopa_scn_Profile_count(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    return (int64_t)g_prof.size();
+}
+int mopa_scn_Profile_read(mopa_scn_profile_record *out, int64_t max_records) {
+    MOPA_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::vector<unsigned long long> counts(g_prof.size());
+    if (!g_prof.empty() && g_prof_counts)
+        MOPA_CUDA(cudaMemcpy(counts.data(), g_prof_counts, g_prof.size() * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < g_prof.size() && (int64_t)i < max_records; ++i) {
+        const ProfRec &r = g_prof[i];
+        float ms = 0.f;
+        MOPA_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        out[i].tag = r.tag; out[i].volume = r.volume; out[i].c_in = r.c_in; out[i].c_out = r.c_out;
+        out[i].rows_out = r.rows_out; out[i].rows_in = r.rows_in;
+        out[i].rules = r.count_slot >= 0 ? (int64_t)counts[r.count_slot] : r.rules;
+        out[i].ms = ms; out[i].reserved = 0;
+    }
+    return 0;
+}
 
 mopa_scn_metadata *mopa_scn_Metadata_new(int dimension, int device) {
     if (dimension != 3) {

@@ -57,6 +57,7 @@ struct Gather {
     int64_t n_out = 0;  // output rows
     int64_t n_in = 0;   // input rows (for bounds/debug)
     int accumulate = 0; // conv_apply: add to the existing output rows instead of overwriting them
+    int op = 0;         // 1 submanifold, 2 convolution, 3 deconvolution (profiling tag only)
 };
 
 int meta_alloc(mopa_scn_metadata *m, void **p, size_t bytes, cudaStream_t s);
@@ -71,8 +72,8 @@ int pack_weights(const float *weight, int volume, int n_in, int n_out, int trans
                  float *packed, cudaStream_t s);
 bool conv_uses_packed(int c_in, int c_out);
 Gather subm_gather(const Level &L);
-Gather child_gather(const Level &fine, const Level &coarse);
-Gather select_gather(const Level &fine, const Level &coarse);
+Gather child_gather(const Level &fine, const Level &coarse, int op = 0);
+Gather select_gather(const Level &fine, const Level &coarse, int op = 0);
 int bn_forward(const float *in, int64_t ld_in, float *out, int64_t ld_out, float *save_mean, float *save_invstd,
                float *running_mean, float *running_var, const float *weight, const float *bias, float eps, float momentum,
                int train, float leakiness, int64_t n_active, int planes, void *workspace, cudaStream_t s);

@@ -121,7 +121,9 @@ static Gather op_gather(const POp &o, const mopa_scn_metadata *m, bool for_dinpu
     const Level &fine = m->levels[down ? o.level_in : o.level_out];
     const Level &coarse = m->levels[down ? o.level_out : o.level_in];
     const bool rows_are_coarse = down != for_dinput;
-    return rows_are_coarse ? child_gather(fine, coarse) : select_gather(fine, coarse);
+    Gather g = rows_are_coarse ? child_gather(fine, coarse) : select_gather(fine, coarse);
+    g.op = down ? 2 : 3;
+    return g;
 }
 
 }  // namespace mopa

@@ -13,10 +13,6 @@ from .. import _lib
 
 _cfg = {"precision": _lib.PREC_TF32}
 
-# bench.py's roofline leg: when this is a list, every conv forward kernel is bracketed by CUDA events on the
-# launching stream and (kind, events, shape info) is appended. None (default) = no instrumentation at all.
-profile_log = None
-
 
 def set_precision(name):
     """'tf32' (default: one TF32 MMA per product) or 'fp32' (3xTF32 split operands: fp32-equivalent, ~3x the MMA work)."""
@@ -241,9 +237,6 @@ class _ConvFunction(Function):
         packed = _pack(w, volume, n_in, n_out, 0, 0)
         prec = _cfg["precision"]
         s = _stream()
-        if profile_log is not None:
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
         if kind == "subm":
             st = L.mopa_scn_SubmanifoldConvolution_updateOutput(metadata._h, sizes[0], filter_size, feats.data_ptr(), ld_in,
                                                                 out.data_ptr(), n_out, w.data_ptr(), _ptr(packed), n_in,
@@ -257,10 +250,6 @@ class _ConvFunction(Function):
                                                        feats.data_ptr(), ld_in, out.data_ptr(), n_out, w.data_ptr(),
                                                        _ptr(packed), n_in, n_out, prec, s)
         _lib.check(st)
-        if profile_log is not None:
-            ev1.record()
-            profile_log.append({"kind": kind, "ev": (ev0, ev1), "metadata": metadata, "size": sizes[0], "volume": volume,
-                                "n_in": n_in, "n_out": n_out, "rows_in": feats.shape[0], "rows_out": n_out_rows})
         ctx.save_for_backward(feats, w)
         ctx.meta, ctx.kind, ctx.sizes, ctx.fs = metadata, kind, sizes, (filter_size, stride)
         return out
