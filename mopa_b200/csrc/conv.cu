@@ -17,38 +17,13 @@
 //   d_weight             : per (k, row chunk): block-local ordered compaction of the chunk's rules, cp.async staging of
 //                          the gathered in/dOut rows, MMA with M = nIn, N = nOut, K = rules; per-chunk partials are
 //                          summed in fixed order by a second kernel (deterministic).
+#include <stdlib.h>
+
 #include "geometry.cuh"
 #include "mopa_scn.h"
+#include "ptx.cuh"
 
 namespace mopa {
-
-// ------------------------------------------------------------------------------------------------ small PTX helpers
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool valid) {
-    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    int sz = valid ? 16 : 0;  // src-size 0 => zero fill
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(sz));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N));
-}
-
-__device__ __forceinline__ int gather_lookup(const Gather &g, int k, int64_t row) {
-    if (g.table) return __ldg(g.table + (int64_t)k * g.ld + row);
-    return (__ldg(g.kidx + row) == k) ? __ldg(g.parent + row) : -1;
-}
 
 // ------------------------------------------------------------------------------------------------ weight packing
 // The contraction axis is cut into chunks of 32 channels (the last one 16 when c_in % 32 == 16); one (offset, chunk) pair
@@ -86,37 +61,6 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float *__restrict__ 
     float v = transpose ? w[((int64_t)ks * n_in0 + co) * n_out0 + ci] : w[((int64_t)ks * n_in0 + ci) * n_out0 + co];
     float hi = __uint_as_float(to_tf32(v));
     packed[idx] = half == 0 ? hi : __uint_as_float(to_tf32(v - hi));
-}
-
-// ------------------------------------------------------------------------------------------------ mbarrier / TMA helpers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    const uint32_t a = smem_u32(bar);
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(a), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ gather-MMA kernel
@@ -611,6 +555,13 @@ __global__ void __launch_bounds__(256) k_dw_reduce(const float *__restrict__ par
 }
 
 // ------------------------------------------------------------------------------------------------ host dispatch
+bool conv_tc_enabled() {  // MOPA_SCN_NO_TC=1 keeps every layer on the mma.sync kernel (A/B measurements)
+    static const bool on = [] {
+        const char *e = getenv("MOPA_SCN_NO_TC");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
 bool conv_uses_packed(int c_in, int c_out) {
     if (c_in % 16 || c_out % 16 || c_in < 16 || c_out < 16) return false;
     const int np = c_out / 16;
@@ -680,6 +631,8 @@ int conv_apply(const Gather &gt, const float *in, int64_t ld_in, float *out, int
         return 0;
     }
     const int split = precision == MOPA_SCN_PREC_FP32;
+    if (!split && conv_tc_enabled() && conv_tc_supported(c_in, c_out))
+        return conv_apply_tc(gt, in, ld_in, out, ld_out, packed, c_in, c_out, s);
     switch (c_out / 16) {
         case 1: return dispatch_np<1>(gt, in, ld_in, out, ld_out, packed, c_in, split, s);
         case 2: return dispatch_np<2>(gt, in, ld_in, out, ld_out, packed, c_in, split, s);
@@ -792,6 +745,8 @@ int pack_weights(const float *weight, int volume, int n_in, int n_out, int trans
     const int c_in = transpose ? n_out : n_in, c_out = transpose ? n_in : n_out;
     MOPA_CHECK(c_in % 16 == 0 && c_out % 16 == 0, "packWeights: channel counts must be multiples of 16");
     const int split = precision == MOPA_SCN_PREC_FP32;
+    if (!split && conv_tc_enabled() && conv_tc_supported(c_in, c_out))
+        return pack_weights_tc(weight, volume, n_in, n_out, transpose, flip, packed, s);
     const int64_t total = (int64_t)volume * n_in * n_out * (split ? 2 : 1);
     k_pack_weights<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(weight, volume, n_in, n_out, transpose, flip, split, packed,
                                                                   total);
@@ -824,7 +779,10 @@ using namespace mopa;
 extern "C" {
 
 int64_t mopa_scn_packedWeightFloats(int volume, int n_in, int n_out, int precision) {
-    return (int64_t)volume * n_in * n_out * (precision == MOPA_SCN_PREC_FP32 ? 2 : 1);
+    // room for either operand orientation in either kernel's layout (the tcgen05 layout pads channels to 32)
+    const int64_t a = (int64_t)volume * n_in * n_out * (precision == MOPA_SCN_PREC_FP32 ? 2 : 1);
+    const int64_t b = (int64_t)volume * round_up(n_in, 32) * round_up(n_out, 32);
+    return a > b ? a : b;
 }
 
 int mopa_scn_packWeights(const float *weight, int volume, int n_in, int n_out, int transpose, int flip, int precision,

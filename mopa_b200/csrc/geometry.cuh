@@ -71,6 +71,14 @@ size_t dw_workspace_bytes(int volume, int n_in, int n_out, int64_t n_rows);
 int pack_weights(const float *weight, int volume, int n_in, int n_out, int transpose, int flip, int precision,
                  float *packed, cudaStream_t s);
 bool conv_uses_packed(int c_in, int c_out);
+// tcgen05 path (conv_tc.cu): TF32 mode, channel counts that are multiples of 16
+bool conv_tc_enabled();
+bool conv_tc_supported(int c_in, int c_out);
+int64_t tc_packed_floats(int volume, int c_in, int c_out);
+int pack_weights_tc(const float *weight, int volume, int n_in, int n_out, int transpose, int flip, float *packed,
+                    cudaStream_t s);
+int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *packed,
+                  int c_in, int c_out, cudaStream_t s);
 Gather subm_gather(const Level &L);
 Gather child_gather(const Level &fine, const Level &coarse, int op = 0);
 Gather select_gather(const Level &fine, const Level &coarse, int op = 0);

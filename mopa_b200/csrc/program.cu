@@ -95,7 +95,7 @@ static int make_layout(const mopa_scn_program *p, const mopa_scn_metadata *m, in
             off += align256((size_t)2 * o.n_in * 4);
         } else {
             const int volume = o.type == OP_SUBM ? 27 : 8;
-            const size_t pk = (size_t)volume * o.n_in * o.n_out * 4 * (precision == MOPA_SCN_PREC_FP32 ? 2 : 1);
+            const size_t pk = (size_t)mopa_scn_packedWeightFloats(volume, o.n_in, o.n_out, precision) * 4;
             if (pk > L.packed_bytes) L.packed_bytes = align256(pk);
             const int64_t rows = m->levels[o.level_out].V;  // d_weight chunks run over the op's OUTPUT rows
             const size_t dw = dw_workspace_bytes(volume, o.n_in, o.n_out, rows);
