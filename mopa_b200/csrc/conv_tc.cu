@@ -2,66 +2,68 @@
 // Same contract as k_gather_mma in conv.cu (replaces [UPSTREAM] SparseConvNet SCN/CUDA/Convolution.cu's per-offset
 // gather-FMA-scatter kernels reached from mopa/models/scn_unet.py:27-28), TF32 precision mode only.
 //
-// Why tcgen05 here: not for FLOPs (the layers are HBM-bound) but for INSTRUCTION economy. With mma.sync every gathered
-// row travels global -> registers -> (cvt) -> MMA fragments and every product comes back as a register fragment that has
-// to be scattered; at ~4 rules per site and offset that costs hundreds of issue slots per 16 rules (ncu: 2.7% of the
-// issued instructions were HMMA). Here a gathered row goes global -> shared memory with cp.async (LDGSTS, no registers),
-// one elected thread issues the MMA straight from shared memory, and a product row comes back as ONE TMEM lane per
-// thread, which that thread adds to its output row.
+// Why tcgen05 here: not for FLOPs (the layers are HBM/L2-bound) but for INSTRUCTION economy. With mma.sync every gathered
+// row travels global -> registers -> cvt -> MMA fragments and the products come back as register fragments; at ~4 rules
+// per site that costs hundreds of issue slots per useful MMA (ncu: 2.7% of the issued instructions were HMMA). Here a
+// gathered row goes global -> shared memory with cp.async (LDGSTS, no registers), one elected thread issues the MMAs
+// straight from shared memory, and the accumulator never leaves TMEM until the tile is finished.
 //
-// CTA = 256 output rows, 10 warps:
-//   warps 0-3  gather   : warp w owns rows [64w, 64w+64). Per filter offset k it compacts the rows that have a rule
-//                         (ballot -> slot = rank), publishes the slot -> (input row, output row) lists, and copies the
-//                         slots' input rows (32 channels = 128 bytes per step) into its quarter (32 slots) of the
-//                         128-row A tile of a ring stage, in the UMMA K-major SWIZZLE_128B layout. More than 32 rules
-//                         per warp and offset (dense clouds; always the centre offset) take a second pass.
-//   warp  8    weights  : one lane streams W[k] chunks (pre-packed in the same swizzled K-major layout) by TMA bulk copy.
-//   warp  9    MMA      : one lane issues tcgen05.mma (M = 128 slots, N = C_out, K = 8 per instruction) into a TMEM
-//                         accumulator (one per offset and pass, NBUF offsets in flight), commits to mbarriers.
-//   warps 4-7  epilogue : warp 4+w reads TMEM lanes 32w.. (its slots), and adds each valid slot's product row to the
-//                         slot's output row of the CTA's fp32 accumulator tile in shared memory. An output row occurs at
-//                         most once per offset and belongs to one warp: plain read-modify-write, fixed order (k ascending).
-// Every output row is written to HBM once, coalesced.
+// Output-stationary, no scatter at all: a CTA owns 256 consecutive OUTPUT rows = two M = 128 accumulator tiles in TMEM
+// (D row = output row, N = C_out columns). For every filter offset k and 32-channel chunk, the A operand tile is
+// "input row of the neighbour at offset k, or zero": rows without a neighbour stay zero in shared memory, so the dense MMA
+// adds nothing for them. The tensor core runs ~6x more MACs than there are rules (a lidar site has ~4 of 27 neighbours),
+// which still costs less time than the HBM floor of every layer; what is saved is all per-rule bookkeeping.
+//
+//   warps 0-3  gather  : warp w owns rows [32w, 32w+32) of each M tile (= TMEM lane quarter w). Per step (k, chunk, tile)
+//                        it reads its 32 neighbour ids (coalesced, prefetched one offset ahead), and for the rows that
+//                        have one copies 128 bytes of the neighbour's row into the A stage (UMMA K-major SWIZZLE_128B
+//                        layout) with cp.async; rows it wrote in the stage's previous use and does not rewrite are
+//                        zeroed again, so a stage is all-zero except for live rules. Up to SA-1 later steps stay in
+//                        flight before a step is fenced (fence.proxy.async) and signalled on its mbarrier.
+//   warp  4    weights : one lane streams W[k] chunks (pre-packed N x K K-major, same swizzle) by TMA bulk copy.
+//   warp  5    MMA     : one lane issues tcgen05.mma (M = 128, N = C_out, K = 8 per instruction, fp32 accumulate in
+//                        TMEM) and commits stage releases to mbarriers.
+//   epilogue           : when the last MMA has retired, warps 0-3 read their TMEM lanes (one output row per thread) and
+//                        write every output row to HBM once (optionally added to what is there).
+// Summation order is fixed (k ascending, chunks ascending, hardware order inside an MMA): results are deterministic.
+#include <stdlib.h>
+
 #include "geometry.cuh"
 #include "mopa_scn.h"
 #include "ptx.cuh"
 
 namespace mopa {
 
-constexpr int kTcRW = 64;            // output rows per gather / epilogue warp
-constexpr int kTcTM = 4 * kTcRW;     // output rows per CTA
+constexpr int kTcTM = 256;            // output rows per CTA (two M = 128 tiles)
 constexpr int kTcThreads = 10 * 32;
-constexpr int kTcListBytes = kTcRW * 4 + kTcRW;  // one list: input rows (int32) + output rows inside the CTA tile (uint8)
-constexpr int kTcChunk = 32;         // input channels per pipeline step (one 128-byte swizzle row)
-constexpr int kTcAStage = 128 * 128; // bytes: 128 slots x 128 bytes
+constexpr int kTcChunk = 32;          // input channels per pipeline step (one 128-byte swizzle row)
+constexpr int kTcAStage = 128 * 128;  // bytes: 128 rows x 128 bytes
+constexpr int kTcMaxSA = 12, kTcMaxSB = 8;
 
-__host__ __device__ constexpr int tc_col_stride(int nt) { return nt <= 16 ? 16 : (nt <= 32 ? 32 : (nt <= 64 ? 64 : 128)); }
-__host__ __device__ constexpr int tc_nbuf(int nt) { return nt <= 64 ? 4 : 2; }  // TMEM accumulators: NBUF offsets x 2 passes
-__host__ __device__ constexpr int tc_tmem_cols(int nt) {
-    return tc_nbuf(nt) * 2 * tc_col_stride(nt) < 32 ? 32 : tc_nbuf(nt) * 2 * tc_col_stride(nt);
+__host__ __device__ inline int tc_tmem_cols(int nt) {  // power of two >= 32 holding two accumulators of nt columns
+    int c = 32;
+    while (c < 2 * nt) c <<= 1;
+    return c;
 }
-__host__ __device__ constexpr int tc_ldo(int nt) { return nt + 4; }  // accumulator tile row stride (floats)
 
-// packed[slice][k][chunk][NT rows x 128 bytes, SWIZZLE_128B]: B operand (N x K, K-major) of one pipeline step.
-// element (n, c) of a chunk = W'[ci = 32 chunk + c][co = slice NT + n], rounded to TF32 (zero for ci >= c_in).
+// packed[k][chunk][NT rows x 128 bytes, SWIZZLE_128B]: B operand (N x K, K-major) of one pipeline step.
+// element (n, c) of a chunk = W'[ci = 32 chunk + c][co = n], rounded to TF32 (zero for ci >= c_in).
 __global__ void __launch_bounds__(256) k_pack_weights_tc(const float *__restrict__ w, int volume, int n_in0, int n_out0,
-                                                         int transpose, int flip, int nt, float *__restrict__ packed,
+                                                         int transpose, int flip, float *__restrict__ packed,
                                                          int64_t total) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int c_in = transpose ? n_out0 : n_in0;
+    const int c_in = transpose ? n_out0 : n_in0, nt = transpose ? n_in0 : n_out0;
     const int nchunk = (c_in + kTcChunk - 1) / kTcChunk;
-    const int64_t per_chunk = (int64_t)nt * kTcChunk, per_k = per_chunk * nchunk, per_slice = per_k * volume;
-    const int slice = (int)(idx / per_slice);
-    int64_t r = idx - (int64_t)slice * per_slice;
-    const int k = (int)(r / per_k);
-    r -= (int64_t)k * per_k;
+    const int64_t per_chunk = (int64_t)nt * kTcChunk, per_k = per_chunk * nchunk;
+    const int k = (int)(idx / per_k);
+    int64_t r = idx - (int64_t)k * per_k;
     const int chunk = (int)(r / per_chunk);
     r -= (int64_t)chunk * per_chunk;
     // r = float index inside the swizzled tile: row n = r / 32, physical 16-byte piece pp = (r % 32) / 4
     const int n = (int)(r >> 5), pp = (int)(r & 31) >> 2, e = (int)(r & 3);
     const int c = ((pp ^ (n & 7)) << 2) + e;  // logical channel inside the chunk
-    const int ci = chunk * kTcChunk + c, co = slice * nt + n;
+    const int ci = chunk * kTcChunk + c, co = n;
     const int ks = flip ? volume - 1 - k : k;
     float v = 0.f;
     if (ci < c_in) v = transpose ? w[((int64_t)ks * n_in0 + co) * n_out0 + ci] : w[((int64_t)ks * n_in0 + ci) * n_out0 + co];
@@ -69,251 +71,182 @@ __global__ void __launch_bounds__(256) k_pack_weights_tc(const float *__restrict
 }
 
 struct TcSmem {  // byte offsets inside the dynamic shared memory block (base aligned to 1024)
-    int a, b, out, lists, cnt, bars, total;
+    int a, b, mask, bars, total;
 };
-// lr = depth of the list / count ring: the gather warps run at most SA + NBUF offsets ahead of the epilogue warps
-__host__ __device__ inline int tc_list_ring(int nt, int sa) { return sa + tc_nbuf(nt) + 1 <= 8 ? 8 : 16; }
 __host__ __device__ inline TcSmem tc_smem_layout(int nt, int sa, int sb) {
-    const int lr = tc_list_ring(nt, sa);
     TcSmem L;
     L.a = 0;
     L.b = L.a + sa * kTcAStage;
-    L.out = L.b + sb * nt * 128;
-    L.lists = L.out + kTcTM * tc_ldo(nt) * 4;
-    L.cnt = L.lists + 4 * lr * kTcListBytes;
-    L.bars = L.cnt + lr * 8 * 4;  // per ring slot: 4 counts + pass count (+ pad)
-    L.total = L.bars + 8 * (2 * 8 + 2 * 4 + 2 * 4) + 16;     // mbarriers: A full/empty [8], B [4], D [4]; tmem pointer
+    L.mask = L.b + sb * nt * 128;
+    L.bars = L.mask + kTcMaxSA * 4 * 36 + 4 * 64;  // per stage and gather warp: rows written last time; current row lists
+    L.total = L.bars + 8 * (2 * kTcMaxSA + 2 * kTcMaxSB + 1) + 16;
     return L;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads)
     k_conv_tc(Gather gt, const float *__restrict__ in, int64_t ld_in, float *__restrict__ out, int64_t ld_out,
-              const float *__restrict__ packed, int c_in, int SA, int SB) {
-    constexpr int LDO = tc_ldo(NT);
-    constexpr int NBUF = tc_nbuf(NT);
-    constexpr int CS = tc_col_stride(NT);
-    constexpr uint32_t IDESC = umma_idesc_tf32(NT);
+              const float *__restrict__ packed, int c_in, int NT, int SA, int SB) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const TcSmem L = tc_smem_layout(NT, SA, SB);
     unsigned char *sA = smem + L.a, *sB = smem + L.b;
-    float *sOut = reinterpret_cast<float *>(smem + L.out);
-    const int LR = tc_list_ring(NT, SA);
-    unsigned char *sLists = smem + L.lists;                      // [warp][LR][kTcListBytes]
-    int32_t *sCnt = reinterpret_cast<int32_t *>(smem + L.cnt);  // [LR][8]: n_w (4), passes, pad
-    uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + L.bars), *a_empty = a_full + 8;
-    uint64_t *b_full = a_empty + 8, *b_empty = b_full + 4;
-    uint64_t *d_full = b_empty + 4, *d_empty = d_full + 4;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(d_empty + 4);
+    unsigned char *sOld = smem + L.mask;             // [SA][4 warps][36]: rows each warp wrote in the stage's last use
+    unsigned char *sList = sOld + kTcMaxSA * 4 * 36;  // [8 warps][32]: current offset's row lists
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + L.bars), *a_empty = a_full + kTcMaxSA;
+    uint64_t *b_full = a_empty + kTcMaxSA, *b_empty = b_full + kTcMaxSB;
+    uint64_t *d_full = b_empty + kTcMaxSB;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(d_full + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = gt.volume;
     const int nchunk = (c_in + kTcChunk - 1) / kTcChunk;
-    packed += (int64_t)blockIdx.y * K * nchunk * NT * kTcChunk;
-    out += (int64_t)blockIdx.y * NT;
+    const int64_t row0 = (int64_t)blockIdx.x * kTcTM;
+    const int n_mt = gt.n_out - row0 > 128 ? 2 : 1;  // M tiles of this CTA that hold rows
+    const uint32_t tmem_cols = (uint32_t)tc_tmem_cols(NT);
 
     if (tid == 0) {
-        for (int i = 0; i < 8; ++i) { mbar_init(a_full + i, 4); mbar_init(a_empty + i, 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
+        for (int i = 0; i < SA; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < SB; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+        mbar_init(d_full, 1);
         mbar_fence_init();
     }
-    if (warp == 9) tmem_alloc(tmem_ptr, tc_tmem_cols(NT));
+    if (warp == 9) tmem_alloc(tmem_ptr, tmem_cols);
+    if (warp < 8) {  // all A stages start all-zero; nothing has been written by any warp yet
+        for (int i = tid; i < SA * kTcAStage / 16; i += 256) reinterpret_cast<float4 *>(sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < kTcMaxSA * 4 * 36; i += 256) sOld[i] = 0;
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ================================================================= gather warps
-        const int w = warp;
-        const int64_t wrow0 = (int64_t)blockIdx.x * kTcTM + (int64_t)w * kTcRW;
-        unsigned char *myLists = sLists + (size_t)w * LR * kTcListBytes;
-        int nv[2], nn[2];
-        auto lookup = [&](int k, int (&v)[2]) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int64_t row = wrow0 + 32 * j + lane;
-                v[j] = (k < K && row < gt.n_out) ? gather_lookup(gt, k, row) : -1;
-            }
-        };
-        lookup(0, nv);
-        int s = 0;          // A-ring step counter (k, chunk, pass)
-        int arrived = 0;    // steps whose copies have landed and been signalled
-        const int DA = SA - 1;  // copies of up to DA later steps may still be in flight when a step is signalled
-        auto signal_upto = [&](int upto) {  // all lanes: their copies of steps < upto are complete
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0)
-                for (int q = arrived; q < upto; ++q) mbar_arrive(a_full + (q % SA));
-            arrived = upto;
-        };
-        for (int k = 0; k < K; ++k) {
-            lookup(k + 1, nn);
-            // ---- ordered compaction: slot = rank of the row among this warp's rows that have a rule at offset k
-            int32_t *lin = reinterpret_cast<int32_t *>(myLists + (k % LR) * kTcListBytes);
-            unsigned char *lrow = reinterpret_cast<unsigned char *>(lin + kTcRW);
-            int n = 0;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const unsigned m = __ballot_sync(0xffffffffu, nv[j] >= 0);
-                if (nv[j] >= 0) {
-                    const int pos = n + __popc(m & ((1u << lane) - 1));
-                    lin[pos] = nv[j];
-                    lrow[pos] = (unsigned char)(w * kTcRW + 32 * j + lane);
-                }
-                n += __popc(m);
-            }
-            nv[0] = nn[0]; nv[1] = nn[1];
-            int32_t *cnt = sCnt + (k % LR) * 8;
-            if (lane == 0) cnt[w] = n;
-            named_barrier_sync(1, 128);  // the four gather warps agree on the number of passes of this offset
-            const int nmax = max(max(cnt[0], cnt[1]), max(cnt[2], cnt[3]));
-            const int P = nmax > 32 ? 2 : 1;
-            if (w == 0 && lane == 0) cnt[4] = P;
+        // warps 0-3 feed M tile 0, warps 4-7 M tile 1; warp w owns tile rows [32 (w & 3), +32) = TMEM lane quarter w & 3
+        const int mt = warp >> 2, wq = warp & 3, grp = lane >> 3, c = lane & 7;  // lane group -> row, lane & 7 -> 16-byte piece
+        const bool live = mt < n_mt;
+        const int64_t row = row0 + 128 * mt + 32 * wq + lane;
+        const bool row_ok = live && row < gt.n_out;
+        unsigned char *myList = sList + warp * 32;  // lanes of the rows that have a rule at the current offset
+        // ring bookkeeping without divisions: this warp's steps are s = 2 j + mt -> stage (2 j + mt) % SA (SA is even)
+        int st = mt, ph = 1;          // stage / parity of the a_empty wait of the next step to issue
+        int nv = row_ok ? gather_lookup(gt, 0, row) : -1, nn = -1;
+        const int n_k = live ? K : 0;
+        for (int k = 0; k < n_k; ++k) {
+            if (k + 1 < K && row_ok) nn = gather_lookup(gt, k + 1, row);
+            const uint32_t m_new = __ballot_sync(0xffffffffu, nv >= 0);
+            const int n = __popc(m_new);
+            if (nv >= 0) myList[__popc(m_new & ((1u << lane) - 1))] = (unsigned char)lane;
             __syncwarp();
             for (int ch = 0; ch < nchunk; ++ch) {
-                const int kc16 = min(kTcChunk, c_in - ch * kTcChunk) / 4;  // valid 16-byte pieces per row
-                for (int p = 0; p < P; ++p, ++s) {
-                    const int st = s % SA;
-                    mbar_wait(a_empty + st, ((s / SA) & 1) ^ 1);
-                    const int np = min(32, n - 32 * p);
-                    unsigned char *tile = sA + (size_t)st * kTcAStage;
-                    const int c = lane & 7;
-                    for (int j = lane >> 3; j < np; j += 4) {
-                        const int idx = lin[32 * p + j];
-                        const int r = 32 * w + j;  // row of the A tile
-                        if (c < kc16)
-                            cp_async16(tile + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4),
-                                       in + (int64_t)idx * ld_in + ch * kTcChunk + 4 * c, true);
-                    }
-                    cp_async_commit();
-                    if (s + 1 - arrived > DA) {  // keep at most DA steps in flight: wait for the oldest, signal it
-                        switch (DA) {
-                            case 1: cp_async_wait_upto<1>(); break;
-                            case 2: cp_async_wait_upto<2>(); break;
-                            case 3: cp_async_wait_upto<3>(); break;
-                            case 4: cp_async_wait_upto<4>(); break;
-                            case 5: cp_async_wait_upto<5>(); break;
-                            case 6: cp_async_wait_upto<6>(); break;
-                            default: cp_async_wait_upto<0>(); break;
-                        }
-                        signal_upto(DA <= 6 ? s + 1 - DA : s + 1);
-                    }
+                const uint32_t pieces = (uint32_t)min(kTcChunk, c_in - ch * kTcChunk) / 4;  // 16-byte pieces per row
+                const float *src0 = in + ch * kTcChunk + 4 * c;
+                mbar_wait(a_empty + st, ph);
+                unsigned char *tile = sA + (size_t)st * kTcAStage + wq * 4096;  // this warp's 32 rows (4 swizzle groups)
+                unsigned char *old = sOld + (st * 4 + wq) * 36;                 // [n, pieces, -, -, rows[32]]
+                // the stage's previous use wrote rows old[4..] x pieces [0, p_old): whatever of that is not rewritten now
+                // (rows m_new x pieces [0, pieces)) goes back to zero: a stage is zero outside its live rules
+                const int n_old = old[0];
+                const uint32_t p_old = old[1];
+                for (int i = grp; i < n_old; i += 4) {
+                    const int r = old[4 + i];
+                    const bool rewritten = ((m_new >> r) & 1u) && (uint32_t)c < pieces;
+                    if ((uint32_t)c < p_old && !rewritten)  // zero fill through the same async path as the copies
+                        cp_async16(tile + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4), in, false);
                 }
+                for (int i0 = 0; i0 < n; i0 += 4) {  // four rows per pass
+                    const int i = i0 + grp;
+                    const int r = i < n ? myList[i] : 0;
+                    const int src = __shfl_sync(0xffffffffu, nv, r);
+                    if (i < n && (uint32_t)c < pieces)
+                        cp_async16(tile + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4), src0 + (int64_t)src * ld_in,
+                                   true);
+                }
+                // every lane: "my copies of this step have landed" arrives on the stage's barrier asynchronously (128
+                // arrivals complete it); the warp never waits for data, so all stages of the ring can be in flight
+                cp_async_mbar_arrive_noinc(a_full + st);
+                if (lane < n) old[4 + lane] = myList[lane];
+                if (lane == 0) { old[0] = (unsigned char)n; old[1] = (unsigned char)pieces; }
+                __syncwarp();
+                st += 2;
+                if (st >= SA) { st -= SA; ph ^= 1; }
             }
+            nv = nn;
         }
-        cp_async_wait_upto<0>();
-        signal_upto(s);
-    } else if (warp < 8) {
-        // ================================================================= epilogue warps
-        const int w = warp - 4;
-        const int64_t wrow0 = (int64_t)blockIdx.x * kTcTM + (int64_t)w * kTcRW;
-        float *myOut = sOut + w * kTcRW * LDO;
-        for (int i = lane; i < kTcRW * LDO / 4; i += 32) reinterpret_cast<float4 *>(myOut)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncwarp();
-        const unsigned char *myLists = sLists + (size_t)w * LR * kTcListBytes;
-        for (int k = 0; k < K; ++k) {
-            const int b = k % NBUF;
-            mbar_wait(d_full + b, (k / NBUF) & 1);
+
+        // ================================================================= epilogue: TMEM -> HBM, one output row per thread
+        if (live) {
+            mbar_wait(d_full, 0);
             tc_fence_after_sync();
-            const int32_t *cnt = sCnt + (k % LR) * 8;
-            const int n = cnt[w], P = cnt[4];
-            const unsigned char *lrow = myLists + (k % LR) * kTcListBytes + kTcRW * 4;
-            for (int p = 0; p < P; ++p) {
-                const int np = min(32, n - 32 * p);
-                if (np <= 0) break;
-                float *orow = lane < np ? sOut + lrow[32 * p + lane] * LDO : nullptr;
-                const uint32_t taddr = tmem_base + ((uint32_t)(32 * w) << 16) + (uint32_t)((b * 2 + p) * CS);
+            float *dst = out + row * ld_out;
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(mt * NT);
+            for (int q = 0; q < NT / 16; ++q) {
+                float v[16];
+                tmem_ld16(taddr + 16 * q, v);  // warp-collective: every lane takes part, also beyond n_out
+                if (row < gt.n_out) {
 #pragma unroll
-                for (int q = 0; q < NT / 16; ++q) {
-                    float v[16];
-                    tmem_ld16(taddr + 16 * q, v);
-                    if (orow) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float4 o = *reinterpret_cast<float4 *>(orow + 16 * q + 4 * e);
-                            o.x += v[4 * e]; o.y += v[4 * e + 1]; o.z += v[4 * e + 2]; o.w += v[4 * e + 3];
-                            *reinterpret_cast<float4 *>(orow + 16 * q + 4 * e) = o;
-                        }
+                    for (int e = 0; e < 4; ++e) {
+                        float4 o = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                        float4 *p = reinterpret_cast<float4 *>(dst + 16 * q + 4 * e);
+                        if (gt.accumulate) { const float4 x = *p; o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w; }
+                        *p = o;
                     }
                 }
             }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(d_empty + b);
-        }
-        __syncwarp();
-        // ---- every output row is written once, coalesced
-        constexpr int F4 = NT / 4;
-        for (int i = lane; i < kTcRW * F4; i += 32) {
-            const int r = i / F4, c = i - r * F4;
-            const int64_t row = wrow0 + r;
-            if (row >= gt.n_out) break;
-            float4 v = *reinterpret_cast<const float4 *>(myOut + r * LDO + 4 * c);
-            float4 *dst = reinterpret_cast<float4 *>(out + row * ld_out + 4 * c);
-            if (gt.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-            *dst = v;
         }
     } else if (warp == 8) {
         // ================================================================= weight producer (TMA bulk copies)
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)NT * 128;
             const int n_steps = K * nchunk;
+            int st = 0, ph = 1;
             for (int sb = 0; sb < n_steps; ++sb) {
-                const int st = sb % SB;
-                mbar_wait(b_empty + st, ((sb / SB) & 1) ^ 1);
+                mbar_wait(b_empty + st, ph);
                 mbar_expect_tx(b_full + st, bytes);
                 tma_load_1d(sB + (size_t)st * bytes, packed + (int64_t)sb * NT * kTcChunk, bytes, b_full + st);
+                if (++st == SB) { st = 0; ph ^= 1; }
             }
         }
     } else {
         // ================================================================= MMA issuer
         if (lane == 0) {
-            const int LRi = LR;
-            (void)LRi;
-            int s = 0, sb = 0;
+            const uint32_t idesc = umma_idesc_tf32(NT);
+            int st = 0, ph = 0, stb = 0, phb = 0;
             for (int k = 0; k < K; ++k) {
-                const int b = k % NBUF;
-                mbar_wait(d_empty + b, ((k / NBUF) & 1) ^ 1);
-                int P = 1;
-                for (int ch = 0; ch < nchunk; ++ch, ++sb) {
-                    const int stb = sb % SB;
-                    mbar_wait(b_full + stb, (sb / SB) & 1);
+                for (int ch = 0; ch < nchunk; ++ch) {
+                    mbar_wait(b_full + stb, phb);
                     const int nk = min(kTcChunk, c_in - ch * kTcChunk) / 8;  // MMAs (K = 8 each) in this chunk
                     const uint32_t b_addr = smem_u32(sB + (size_t)stb * NT * 128);
-                    for (int p = 0; p < P; ++p, ++s) {
-                        const int st = s % SA;
-                        mbar_wait(a_full + st, (s / SA) & 1);
-                        if (ch == 0 && p == 0) P = *(volatile int32_t *)(sCnt + (k % LR) * 8 + 4);
-                        tc_fence_after_sync();
-                        const uint32_t a_addr = smem_u32(sA + (size_t)st * kTcAStage);
-                        const uint32_t d = tmem_base + (uint32_t)((b * 2 + p) * CS);
-                        for (int j = 0; j < nk; ++j)
-                            umma_tf32(d, umma_desc_sw128(a_addr + 32 * j), umma_desc_sw128(b_addr + 32 * j), IDESC,
-                                      (ch > 0 || j > 0) ? 1u : 0u);
-                        umma_commit(a_empty + st);
+                    for (int mt = 0; mt < 2; ++mt) {  // stage order: step 2 j + mt, also when only tile 0 is live
+                        if (mt < n_mt) {
+                            mbar_wait(a_full + st, ph);
+                            fence_proxy_async_smem();  // the gather warps' cp.async writes (generic proxy) -> UMMA reads
+                            tc_fence_after_sync();
+                            const uint32_t a_addr = smem_u32(sA + (size_t)st * kTcAStage);
+                            const uint32_t d = tmem_base + (uint32_t)(mt * NT);
+                            for (int j = 0; j < nk; ++j)
+                                umma_tf32(d, umma_desc_sw128(a_addr + 32 * j), umma_desc_sw128(b_addr + 32 * j), idesc,
+                                          (k > 0 || ch > 0 || j > 0) ? 1u : 0u);
+                            umma_commit(a_empty + st);
+                        }
+                        if (++st == SA) { st = 0; ph ^= 1; }
                     }
                     umma_commit(b_empty + stb);
+                    if (++stb == SB) { stb = 0; phb ^= 1; }
                 }
-                umma_commit(d_full + b);
             }
+            umma_commit(d_full);
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, tc_tmem_cols(NT));
+    if (warp == 9) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-int tc_col_splits(int c_out) {  // slices of at most 112 output channels; 0 = not on the tcgen05 path
-    if (c_out % 16 || c_out < 16) return 0;
-    const int np = c_out / 16;
-    if (np <= 7) return 1;
-    if (np % 2 == 0 && np / 2 <= 7) return 2;
-    return 0;
+bool conv_tc_supported(int c_in, int c_out) {
+    return c_in % 16 == 0 && c_in >= 16 && c_out % 16 == 0 && c_out >= 16 && c_out <= 256;
 }
-bool conv_tc_supported(int c_in, int c_out) { return c_in % 16 == 0 && c_in >= 16 && tc_col_splits(c_out) > 0; }
 
 int64_t tc_packed_floats(int volume, int c_in, int c_out) {
     return (int64_t)volume * ceil_div(c_in, kTcChunk) * kTcChunk * c_out;
@@ -322,50 +255,37 @@ int64_t tc_packed_floats(int volume, int c_in, int c_out) {
 int pack_weights_tc(const float *weight, int volume, int n_in, int n_out, int transpose, int flip, float *packed,
                     cudaStream_t s) {
     const int c_in = transpose ? n_out : n_in, c_out = transpose ? n_in : n_out;
-    const int cs = tc_col_splits(c_out);
-    MOPA_CHECK(cs > 0 && c_in % 16 == 0, "packWeights: shape is not on the tcgen05 path");
+    MOPA_CHECK(conv_tc_supported(c_in, c_out), "packWeights: shape is not on the tcgen05 path");
     const int64_t total = tc_packed_floats(volume, c_in, c_out);
-    k_pack_weights_tc<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(weight, volume, n_in, n_out, transpose, flip, c_out / cs,
-                                                                    packed, total);
-    MOPA_LAUNCHED();
-    return 0;
-}
-
-template <int NT>
-static int launch_conv_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out,
-                          const float *packed, int c_in, int col_splits, cudaStream_t s) {
-    // ring depths: as many A stages as fit beside the accumulator tile (two CTAs per SM while the tile is small)
-    const int sb = NT <= 64 ? 3 : 2;
-    const size_t cap = NT <= 32 ? (size_t)113 * 1024 : (size_t)226 * 1024;
-    int sa = 8;
-    while (sa > 2 && (size_t)tc_smem_layout(NT, sa, sb).total + 1024 > cap) --sa;
-    if (sa > 7) sa = 7;
-    const size_t smem = (size_t)tc_smem_layout(NT, sa, sb).total + 1024;
-    auto kern = k_conv_tc<NT>;
-    static bool configured = false;
-    if (!configured) {
-        MOPA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
-    }
-    dim3 grid((unsigned)ceil_div(gt.n_out, kTcTM), (unsigned)col_splits);
-    kern<<<grid, kTcThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, sa, sb);
+    k_pack_weights_tc<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(weight, volume, n_in, n_out, transpose, flip, packed,
+                                                                    total);
     MOPA_LAUNCHED();
     return 0;
 }
 
 int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *packed,
                   int c_in, int c_out, cudaStream_t s) {
-    const int cs = tc_col_splits(c_out);
-    switch (c_out / cs) {
-        case 16: return launch_conv_tc<16>(gt, in, ld_in, out, ld_out, packed, c_in, cs, s);
-        case 32: return launch_conv_tc<32>(gt, in, ld_in, out, ld_out, packed, c_in, cs, s);
-        case 48: return launch_conv_tc<48>(gt, in, ld_in, out, ld_out, packed, c_in, cs, s);
-        case 64: return launch_conv_tc<64>(gt, in, ld_in, out, ld_out, packed, c_in, cs, s);
-        case 80: return launch_conv_tc<80>(gt, in, ld_in, out, ld_out, packed, c_in, cs, s);
-        case 96: return launch_conv_tc<96>(gt, in, ld_in, out, ld_out, packed, c_in, cs, s);
-        case 112: return launch_conv_tc<112>(gt, in, ld_in, out, ld_out, packed, c_in, cs, s);
+    const int nt = c_out;
+    // ring depths. An A stage is 16 KB but carries only the few rows that have a rule at that offset, so the gather bytes
+    // in flight are set by the NUMBER of stages (kept even: tile 0 uses the even stages, tile 1 the odd ones).
+    static const int want_ctas = [] { const char *e = getenv("MOPA_TC_CTAS"); return e ? atoi(e) : 2; }();
+    static const int want_sb = [] { const char *e = getenv("MOPA_TC_SB"); return e ? atoi(e) : 4; }();
+    int sb = want_sb < 2 ? 2 : (want_sb > kTcMaxSB ? kTcMaxSB : want_sb);
+    while (sb > 2 && (size_t)sb * nt * 128 > (size_t)64 * 1024) --sb;
+    const bool two = want_ctas >= 2 && tc_tmem_cols(nt) <= 256 && nt <= 64;
+    const size_t cap = two ? (size_t)113 * 1024 : (size_t)226 * 1024;
+    int sa = kTcMaxSA;
+    while (sa > 4 && (size_t)tc_smem_layout(nt, sa, sb).total + 1024 > cap) sa -= 2;
+    const size_t smem = (size_t)tc_smem_layout(nt, sa, sb).total + 1024;
+    static bool configured = false;
+    if (!configured) {
+        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
     }
-    MOPA_FAIL("unreachable tcgen05 conv shape");
+    dim3 grid((unsigned)ceil_div(gt.n_out, kTcTM));
+    k_conv_tc<<<grid, kTcThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb);
+    MOPA_LAUNCHED();
+    return 0;
 }
 
 }  // namespace mopa

@@ -22,6 +22,10 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src,
     int sz = valid ? 16 : 0;  // src-size 0 => zero fill
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(sz));
 }
+// arrive on `bar` (without incrementing its pending count) once all cp.async copies this thread has issued so far have landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
