@@ -83,7 +83,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int nt, int sa, int sb) {
     return L;
 }
 
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcThreads, 2)
     k_conv_tc(Gather gt, const float *__restrict__ in, int64_t ld_in, float *__restrict__ out, int64_t ld_out,
               const float *__restrict__ packed, int c_in, int NT, int SA, int SB) {
     extern __shared__ unsigned char smem_dyn[];
@@ -127,46 +127,52 @@ __global__ void __launch_bounds__(kTcThreads)
         const bool live = mt < n_mt;
         const int64_t row = row0 + 128 * mt + 32 * wq + lane;
         const bool row_ok = live && row < gt.n_out;
-        unsigned char *myList = sList + warp * 32;  // lanes of the rows that have a rule at the current offset
+        // everything below addresses shared memory through 32-bit shared-window addresses
+        const uint32_t list_a = smem_u32(sList) + warp * 32;  // lanes of the rows that have a rule at the current offset
+        const uint32_t tile0_a = smem_u32(sA) + wq * 4096;     // + stage * 16 KB: this warp's 32 rows (4 swizzle groups)
+        const uint32_t old0_a = smem_u32(sOld) + wq * 36;      // + stage * 144: [n | pieces << 8, rows[32]] of the last use
+        const uint32_t full0_a = smem_u32(a_full), empty0_a = smem_u32(a_empty);
         // ring bookkeeping without divisions: this warp's steps are s = 2 j + mt -> stage (2 j + mt) % SA (SA is even)
-        int st = mt, ph = 1;          // stage / parity of the a_empty wait of the next step to issue
+        int st = mt;
+        uint32_t ph = 1;  // parity of the a_empty wait of the next step to issue
         int nv = row_ok ? gather_lookup(gt, 0, row) : -1, nn = -1;
         const int n_k = live ? K : 0;
+        const uint32_t lt_mask = (1u << lane) - 1;
         for (int k = 0; k < n_k; ++k) {
             if (k + 1 < K && row_ok) nn = gather_lookup(gt, k + 1, row);
             const uint32_t m_new = __ballot_sync(0xffffffffu, nv >= 0);
             const int n = __popc(m_new);
-            if (nv >= 0) myList[__popc(m_new & ((1u << lane) - 1))] = (unsigned char)lane;
+            if (nv >= 0) sts_u8(list_a + __popc(m_new & lt_mask), lane);
             __syncwarp();
-            for (int ch = 0; ch < nchunk; ++ch) {
+            const float *src = in + 4 * c;
+            for (int ch = 0; ch < nchunk; ++ch, src += kTcChunk) {
                 const uint32_t pieces = (uint32_t)min(kTcChunk, c_in - ch * kTcChunk) / 4;  // 16-byte pieces per row
-                const float *src0 = in + ch * kTcChunk + 4 * c;
-                mbar_wait(a_empty + st, ph);
-                unsigned char *tile = sA + (size_t)st * kTcAStage + wq * 4096;  // this warp's 32 rows (4 swizzle groups)
-                unsigned char *old = sOld + (st * 4 + wq) * 36;                 // [n, pieces, -, -, rows[32]]
-                // the stage's previous use wrote rows old[4..] x pieces [0, p_old): whatever of that is not rewritten now
+                mbar_wait_s(empty0_a + 8 * st, ph);
+                const uint32_t tile_a = tile0_a + st * kTcAStage, old_a = old0_a + st * 144;
+                // the stage's previous use wrote rows old[..] x pieces [0, p_old): whatever of that is not rewritten now
                 // (rows m_new x pieces [0, pieces)) goes back to zero: a stage is zero outside its live rules
-                const int n_old = old[0];
-                const uint32_t p_old = old[1];
+                const uint32_t hdr = lds_u32(old_a);
+                const int n_old = hdr & 0xff;
+                const uint32_t p_old = hdr >> 8;
                 for (int i = grp; i < n_old; i += 4) {
-                    const int r = old[4 + i];
+                    const uint32_t r = lds_u8(old_a + 4 + i);
                     const bool rewritten = ((m_new >> r) & 1u) && (uint32_t)c < pieces;
                     if ((uint32_t)c < p_old && !rewritten)  // zero fill through the same async path as the copies
-                        cp_async16(tile + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4), in, false);
+                        cp_async16_s(tile_a + r * 128 + ((c ^ (r & 7)) << 4), in, 0);
                 }
                 for (int i0 = 0; i0 < n; i0 += 4) {  // four rows per pass
                     const int i = i0 + grp;
-                    const int r = i < n ? myList[i] : 0;
-                    const int src = __shfl_sync(0xffffffffu, nv, r);
+                    const uint32_t r = i < n ? lds_u8(list_a + i) : 0;
+                    const int srow = __shfl_sync(0xffffffffu, nv, r);
                     if (i < n && (uint32_t)c < pieces)
-                        cp_async16(tile + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4), src0 + (int64_t)src * ld_in,
-                                   true);
+                        cp_async16_s(tile_a + r * 128 + ((c ^ (r & 7)) << 4), src + (int64_t)srow * ld_in, 16);
                 }
                 // every lane: "my copies of this step have landed" arrives on the stage's barrier asynchronously (128
                 // arrivals complete it); the warp never waits for data, so all stages of the ring can be in flight
-                cp_async_mbar_arrive_noinc(a_full + st);
-                if (lane < n) old[4 + lane] = myList[lane];
-                if (lane == 0) { old[0] = (unsigned char)n; old[1] = (unsigned char)pieces; }
+                cp_async_mbar_arrive_noinc_s(full0_a + 8 * st);
+                __syncwarp();  // all lanes have read the old record
+                if (lane < n) sts_u8(old_a + 4 + lane, lds_u8(list_a + lane));
+                if (lane == 0) sts_u32(old_a, (uint32_t)n | (pieces << 8));
                 __syncwarp();
                 st += 2;
                 if (st >= SA) { st -= SA; ph ^= 1; }
