@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libmopa_scn.so")
-SOURCES = ["geometry.cu", "conv.cu", "conv_tc.cu", "bn_io.cu", "program.cu"]
+SOURCES = ["geometry.cu", "conv.cu", "conv_tc.cu", "conv_dw_tc.cu", "bn_io.cu", "program.cu"]
 HEADERS = ["common.cuh", "geometry.cuh", "ptx.cuh"]
 
 

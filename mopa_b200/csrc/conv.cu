@@ -675,7 +675,12 @@ static DwPlan dw_plan(int volume, int n_in, int n_out, int64_t n_rows) {
 }
 
 size_t dw_workspace_bytes(int volume, int n_in, int n_out, int64_t n_rows) {
-    return dw_plan(volume, n_in, n_out, n_rows).partial_bytes + 256;
+    size_t b = dw_plan(volume, n_in, n_out, n_rows).partial_bytes;
+    if (dw_tc_supported(n_in, n_out)) {
+        const size_t t = dw_tc_workspace_bytes(volume, n_in, n_out, n_rows);
+        if (t > b) b = t;
+    }
+    return b + 256;
 }
 
 template <int BPW, bool SPLIT>
@@ -713,6 +718,11 @@ int conv_dweight(const Gather &gt, const float *in, int64_t ld_in, const float *
     } prof_guard{prof, s};
     float *partial = reinterpret_cast<float *>(workspace);
     const bool fast = p.mma && aligned16(in) && aligned16(dout) && ld_in % 4 == 0 && ld_dout % 4 == 0;
+    if (precision == MOPA_SCN_PREC_TF32 && dw_tc_enabled() && dw_tc_supported(n_in, n_out) && aligned16(in) &&
+        aligned16(dout) && ld_in % 4 == 0 && ld_dout % 4 == 0) {
+        MOPA_CHECK(workspace_bytes >= dw_tc_workspace_bytes(gt.volume, n_in, n_out, gt.n_out), "backward workspace too small");
+        return conv_dweight_tc(gt, in, ld_in, dout, ld_dout, dw, n_in, n_out, partial, s);
+    }
     if (fast) {
         const int center = gt.volume == 27 && gt.table ? 13 : -1;
         const bool split = precision == MOPA_SCN_PREC_FP32;

@@ -39,10 +39,11 @@ constexpr int kTcThreads = 10 * 32;
 constexpr int kTcChunk = 32;          // input channels per pipeline step (one 128-byte swizzle row)
 constexpr int kTcAStage = 128 * 128;  // bytes: 128 rows x 128 bytes
 constexpr int kTcMaxSA = 12, kTcMaxSB = 8;
+constexpr int kTcLook = 6;          // neighbour ids are looked up this many offsets ahead
 
-__host__ __device__ inline int tc_tmem_cols(int nt) {  // power of two >= 32 holding two accumulators of nt columns
+__host__ __device__ inline int tc_tmem_cols(int nt, int tpc = 2) {  // power of two >= 32 holding tpc accumulators of nt columns
     int c = 32;
-    while (c < 2 * nt) c <<= 1;
+    while (c < tpc * nt) c <<= 1;
     return c;
 }
 
@@ -85,7 +86,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int nt, int sa, int sb) {
 
 __global__ void __launch_bounds__(kTcThreads, 2)
     k_conv_tc(Gather gt, const float *__restrict__ in, int64_t ld_in, float *__restrict__ out, int64_t ld_out,
-              const float *__restrict__ packed, int c_in, int NT, int SA, int SB) {
+              const float *__restrict__ packed, int c_in, int NT, int SA, int SB, int TPC) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const TcSmem L = tc_smem_layout(NT, SA, SB);
@@ -100,9 +101,11 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = gt.volume;
     const int nchunk = (c_in + kTcChunk - 1) / kTcChunk;
-    const int64_t row0 = (int64_t)blockIdx.x * kTcTM;
-    const int n_mt = gt.n_out - row0 > 128 ? 2 : 1;  // M tiles of this CTA that hold rows
-    const uint32_t tmem_cols = (uint32_t)tc_tmem_cols(NT);
+    // TPC = M tiles per CTA: 2 for the large levels; 1 for levels too small to fill the GPU with 256-row CTAs (twice
+    // the CTAs, and the whole stage ring serves the one tile)
+    const int64_t row0 = (int64_t)blockIdx.x * (128 * TPC);
+    const int n_mt = (TPC == 2 && gt.n_out - row0 > 128) ? 2 : 1;  // M tiles of this CTA that hold rows
+    const uint32_t tmem_cols = (uint32_t)tc_tmem_cols(NT, TPC);
 
     if (tid == 0) {
         for (int i = 0; i < SA; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
@@ -132,14 +135,25 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         const uint32_t tile0_a = smem_u32(sA) + wq * 4096;     // + stage * 16 KB: this warp's 32 rows (4 swizzle groups)
         const uint32_t old0_a = smem_u32(sOld) + wq * 36;      // + stage * 144: [n | pieces << 8, rows[32]] of the last use
         const uint32_t full0_a = smem_u32(a_full), empty0_a = smem_u32(a_empty);
-        // ring bookkeeping without divisions: this warp's steps are s = 2 j + mt -> stage (2 j + mt) % SA (SA is even)
+        // ring bookkeeping without divisions: this warp's steps are s = TPC j + mt -> stage s % SA (SA even when TPC = 2)
         int st = mt;
         uint32_t ph = 1;  // parity of the a_empty wait of the next step to issue
-        int nv = row_ok ? gather_lookup(gt, 0, row) : -1, nn = -1;
         const int n_k = live ? K : 0;
         const uint32_t lt_mask = (1u << lane) - 1;
-        for (int k = 0; k < n_k; ++k) {
-            if (k + 1 < K && row_ok) nn = gather_lookup(gt, k + 1, row);
+        // neighbour ids are fetched kTcLook offsets ahead (a ring of registers with static indices: the k loop is unrolled
+        // kTcLook times). One offset ahead was not enough: a step is shorter than an L2/HBM round trip, and ncu showed the
+        // gather warps spending most of their time on the scoreboard of this load.
+        int sel_k = -2, sel_p = -1;  // select mode: the row's only offset and its source row
+        if (!gt.table && row_ok) { sel_k = __ldg(gt.kidx + row); sel_p = __ldg(gt.parent + row); }
+        auto look = [&](int k) -> int {
+            if (!row_ok || k >= K) return -1;
+            if (gt.table) return __ldg(gt.table + (int64_t)k * gt.ld + row);
+            return sel_k == k ? sel_p : -1;
+        };
+        int nq[kTcLook];
+#pragma unroll
+        for (int u = 0; u < kTcLook; ++u) nq[u] = look(u);
+        auto step = [&](const int nv) {
             const uint32_t m_new = __ballot_sync(0xffffffffu, nv >= 0);
             const int n = __popc(m_new);
             if (nv >= 0) sts_u8(list_a + __popc(m_new & lt_mask), lane);
@@ -174,10 +188,19 @@ __global__ void __launch_bounds__(kTcThreads, 2)
                 if (lane < n) sts_u8(old_a + 4 + lane, lds_u8(list_a + lane));
                 if (lane == 0) sts_u32(old_a, (uint32_t)n | (pieces << 8));
                 __syncwarp();
-                st += 2;
+                st += TPC;
                 if (st >= SA) { st -= SA; ph ^= 1; }
             }
-            nv = nn;
+        };
+        for (int k0 = 0; k0 < n_k; k0 += kTcLook) {
+#pragma unroll
+            for (int u = 0; u < kTcLook; ++u) {
+                if (k0 + u < n_k) {  // warp-uniform
+                    const int nv = nq[u];
+                    nq[u] = look(k0 + u + kTcLook);
+                    step(nv);
+                }
+            }
         }
 
         // ================================================================= epilogue: TMEM -> HBM, one output row per thread
@@ -227,7 +250,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
                     mbar_wait(b_full + stb, phb);
                     const int nk = min(kTcChunk, c_in - ch * kTcChunk) / 8;  // MMAs (K = 8 each) in this chunk
                     const uint64_t b_desc = desc_hi | (uint64_t)((smem_u32(sB + (size_t)stb * NT * 128) & 0x3FFFFu) >> 4);
-                    for (int mt = 0; mt < 2; ++mt) {  // stage order: step 2 j + mt, also when only tile 0 is live
+                    for (int mt = 0; mt < TPC; ++mt) {  // stage order: step TPC j + mt, also when only tile 0 is live
                         if (mt < n_mt) {
                             mbar_wait(a_full + st, ph);
                             fence_proxy_async_smem();  // the gather warps' cp.async writes (generic proxy) -> UMMA reads
@@ -282,23 +305,35 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
                   int c_in, int c_out, cudaStream_t s) {
     const int nt = c_out;
     // ring depths. An A stage is 16 KB but carries only the few rows that have a rule at that offset, so the gather bytes
-    // in flight are set by the NUMBER of stages (kept even: tile 0 uses the even stages, tile 1 the odd ones).
+    // in flight are set by the NUMBER of stages (kept even for two-tile CTAs: tile 0 uses the even stages, tile 1 the odd).
     static const int want_ctas = [] { const char *e = getenv("MOPA_TC_CTAS"); return e ? atoi(e) : 2; }();
     static const int want_sb = [] { const char *e = getenv("MOPA_TC_SB"); return e ? atoi(e) : 4; }();
+    static const int want_tpc = [] { const char *e = getenv("MOPA_TC_TPC"); return e ? atoi(e) : 0; }();
+    // one M tile per CTA while 256-row CTAs would leave CTA slots (2 per SM) empty
+    const int tpc = want_tpc ? want_tpc : (ceil_div(gt.n_out, kTcTM) >= 2 * kNumSMs ? 2 : 1);
     int sb = want_sb < 2 ? 2 : (want_sb > kTcMaxSB ? kTcMaxSB : want_sb);
-    while (sb > 2 && (size_t)sb * nt * 128 > (size_t)64 * 1024) --sb;
-    const bool two = want_ctas >= 2 && tc_tmem_cols(nt) <= 256 && nt <= 64;
-    const size_t cap = two ? (size_t)113 * 1024 : (size_t)226 * 1024;
-    int sa = kTcMaxSA;
-    while (sa > 4 && (size_t)tc_smem_layout(nt, sa, sb).total + 1024 > cap) sa -= 2;
+    while (sb > 2 && (size_t)sb * nt * 128 > (size_t)(tpc == 2 ? 64 : 32) * 1024) --sb;
+    // two CTAs per SM when that helps: not when the whole grid fits one CTA per SM anyway (then the one CTA gets all stages)
+    bool two = want_ctas >= 2 && tc_tmem_cols(nt, tpc) <= 256 && (nt <= 64 || tpc == 1) &&
+               ceil_div(gt.n_out, 128 * tpc) > kNumSMs;
+    int sa = 0;
+    size_t cap = 0;
+    for (;;) {
+        cap = two ? (size_t)113 * 1024 : (size_t)226 * 1024;
+        sa = kTcMaxSA;
+        while (sa > 2 && (size_t)tc_smem_layout(nt, sa, sb).total + 1024 > cap) sa -= tpc;
+        if (!two || sa >= 4) break;
+        two = false;  // too few stages at two CTAs per SM: take the whole SM
+    }
+    MOPA_CHECK((size_t)tc_smem_layout(nt, sa, sb).total + 1024 <= cap && sa >= 2, "conv_tc: shared memory layout does not fit");
     const size_t smem = (size_t)tc_smem_layout(nt, sa, sb).total + 1024;
     static bool configured = false;
     if (!configured) {
         MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    dim3 grid((unsigned)ceil_div(gt.n_out, kTcTM));
-    k_conv_tc<<<grid, kTcThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb);
+    dim3 grid((unsigned)ceil_div(gt.n_out, 128 * tpc));
+    k_conv_tc<<<grid, kTcThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc);
     MOPA_LAUNCHED();
     return 0;
 }

@@ -79,6 +79,12 @@ int pack_weights_tc(const float *weight, int volume, int n_in, int n_out, int tr
                     cudaStream_t s);
 int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *packed,
                   int c_in, int c_out, cudaStream_t s);
+// tcgen05 d_weight (conv_dw_tc.cu): TF32 mode, channel counts that are multiples of 16
+bool dw_tc_enabled();
+bool dw_tc_supported(int n_in, int n_out);
+size_t dw_tc_workspace_bytes(int volume, int n_in, int n_out, int64_t n_rows);
+int conv_dweight_tc(const Gather &gt, const float *in, int64_t ld_in, const float *dout, int64_t ld_dout, float *dw,
+                    int n_in, int n_out, float *partial, cudaStream_t s);
 Gather subm_gather(const Level &L);
 Gather child_gather(const Level &fine, const Level &coarse, int op = 0);
 Gather select_gather(const Level &fine, const Level &coarse, int op = 0);
