@@ -3,6 +3,8 @@
 // mopa/models/scn_unet.py:26,29,30 and from scn.UNet's BatchNormLeakyReLU layers.
 // All of these are pure HBM streaming kernels: 128-bit accesses along the plane axis, grid sized from the SM count,
 // per-block partial statistics combined in fixed order by the last block to finish (deterministic, no float atomics).
+#include <stdlib.h>
+
 #include "geometry.cuh"
 #include "mopa_scn.h"
 
@@ -13,7 +15,11 @@ constexpr int kBnMaxBlocks = 4 * kNumSMs;
 constexpr int kBnMaxPlanes = 256;
 // workspace layout (floats): [0] block counter (int), [8 .. 8+2C) gradMean / k of the backward pass,
 // [8 + 512 ...) 2C fp64 accumulators (8-byte aligned). Zero between calls.
-__host__ __device__ inline size_t bn_ws_floats(int) { return 8 + 2 * (size_t)kBnMaxPlanes + 2 * 2 * (size_t)kBnMaxPlanes; }
+// The fused (single cooperative kernel) path keeps its own block further up: [kBnFusedOff] parity (int), [+2], [+3] arrival
+// counters of the two parities, [+8 ...) two sets of 2 * 256 fp64 accumulators. A call uses the set its parity selects
+// and clears the other one for the next call, so nothing has to be zeroed between kernels.
+constexpr int kBnFusedOff = 1560;
+__host__ __device__ inline size_t bn_ws_floats(int) { return kBnFusedOff + 8 + 2 * 2 * 2 * (size_t)kBnMaxPlanes; }
 __device__ __forceinline__ double *bn_ws_acc(float *ws) { return reinterpret_cast<double *>(ws + 8 + 2 * kBnMaxPlanes); }
 
 template <int VEC>
@@ -215,6 +221,195 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float *__restrict__ 
     }
 }
 
+struct BnShapeArgs {
+    const float *x; int64_t ld_x; const float *dout; int64_t ld_dout; float *out; int64_t ld_out; int64_t n; int planes;
+    float *ws; const float *mean_in; const float *invstd_in; const float *weight; const float *bias; float leakiness;
+    int train; float eps; float momentum; float *save_mean; float *save_invstd; float *running_mean; float *running_var;
+    float *d_weight; float *d_bias; int accumulate;
+};
+// ---- single-kernel BatchNorm (train forward, and backward): statistics, a grid-wide barrier, then the apply pass over
+// the same slab of rows (second read comes from L2). Launched cooperatively so that all blocks are co-resident.
+// Replaces [UPSTREAM] BatchNormalization_ForwardPass / _BackwardPass (two reduction kernels + elementwise).
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <int VEC, bool BWD>
+__global__ void __launch_bounds__(256) k_bn_fused(const float *__restrict__ x, int64_t ld_x, const float *__restrict__ dout,
+                                                  int64_t ld_dout, float *__restrict__ out, int64_t ld_out, int64_t n,
+                                                  int planes, float *__restrict__ ws, const float *__restrict__ mean_in,
+                                                  const float *__restrict__ invstd_in, const float *__restrict__ weight,
+                                                  const float *__restrict__ bias, float leakiness, int train, float eps,
+                                                  float momentum, float *__restrict__ save_mean,
+                                                  float *__restrict__ save_invstd, float *__restrict__ running_mean,
+                                                  float *__restrict__ running_var, float *__restrict__ d_weight,
+                                                  float *__restrict__ d_bias, int accumulate) {
+    extern __shared__ float sred[];  // [blockDim.y][2 * planes]
+    int *hdr = reinterpret_cast<int *>(ws + kBnFusedOff);
+    const int par = *reinterpret_cast<volatile int *>(hdr) & 1;
+    double *acc = reinterpret_cast<double *>(ws + kBnFusedOff + 8) + par * 2 * kBnMaxPlanes;
+    unsigned *ctr = reinterpret_cast<unsigned *>(hdr) + 2 + par;
+    const int c0 = threadIdx.x * VEC;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    const int64_t rpb = ceil_div(n, (int64_t)gridDim.x);
+    const int64_t r0 = (int64_t)blockIdx.x * rpb, r1 = min(n, r0 + rpb);
+    const int64_t stride = blockDim.y;
+    float s1[VEC], s2[VEC], ref[VEC], sc[VEC], sh[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        s1[e] = s2[e] = 0.f;
+        if (BWD) {
+            ref[e] = mean_in[c0 + e];
+            sc[e] = invstd_in[c0 + e] * weight[c0 + e];
+            sh[e] = bias[c0 + e] - ref[e] * sc[e];
+        } else {
+            ref[e] = x[c0 + e];
+        }
+    }
+    auto accumulate_row = [&](const float (&v)[VEC], const float (&d)[VEC]) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            if (BWD) {
+                const float y = fmaf(v[e], sc[e], sh[e]);
+                const float dm = y > 0.f ? d[e] : d[e] * leakiness;
+                s1[e] += dm;
+                s2[e] = fmaf(v[e] - ref[e], dm, s2[e]);
+            } else {
+                const float dv = v[e] - ref[e];
+                s1[e] += dv;
+                s2[e] = fmaf(dv, dv, s2[e]);
+            }
+        }
+    };
+    int64_t r = r0 + threadIdx.y;
+    for (; r + 3 * stride < r1; r += 4 * stride) {
+        float v[4][VEC], d[4][VEC];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            Vec<VEC>::get(x + (r + q * stride) * ld_x + c0, v[q]);
+            if (BWD) Vec<VEC>::get(dout + (r + q * stride) * ld_dout + c0, d[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) accumulate_row(v[q], d[q]);
+    }
+    for (; r < r1; r += stride) {
+        float v[VEC], d[VEC];
+        Vec<VEC>::get(x + r * ld_x + c0, v);
+        if (BWD) Vec<VEC>::get(dout + r * ld_dout + c0, d);
+        accumulate_row(v, d);
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        sred[threadIdx.y * 2 * planes + c0 + e] = s1[e];
+        sred[threadIdx.y * 2 * planes + planes + c0 + e] = s2[e];
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * planes; i += nthr) {
+        float s = 0.f;
+        for (int y = 0; y < (int)blockDim.y; ++y) s += sred[y * 2 * planes + i];
+        atomicAdd(acc + i, (double)s);
+    }
+    // ---- grid-wide barrier (all blocks are resident: cooperative launch)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        atomicAdd(ctr, 1u);
+        while (ld_acquire_u32(ctr) < gridDim.x) {}
+    }
+    __syncthreads();
+    // ---- per-plane coefficients from the fp64 sums
+    const double dn = (double)n;
+    float gm[VEC], kk[VEC], mu[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        const int c = c0 + e;
+        const double a = __ldcg(acc + c), b = __ldcg(acc + planes + c);
+        const bool writer = blockIdx.x == 0 && threadIdx.y == 0;
+        if (!BWD) {
+            const double mean = (double)ref[e] + a / dn;
+            double m2 = b - a * a / dn;  // sum (x - mean)^2
+            if (m2 < 0.0) m2 = 0.0;
+            const float invstd = (float)(1.0 / sqrt(m2 / dn + (double)eps));
+            sc[e] = invstd * weight[c];
+            sh[e] = bias[c] - (float)mean * sc[e];
+            if (writer) {
+                save_mean[c] = (float)mean;
+                save_invstd[c] = invstd;
+                running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * (float)mean;
+                running_var[c] = momentum * running_var[c] + (1.f - momentum) * (float)(m2 / (n > 1 ? dn - 1.0 : 1.0));
+            }
+        } else {
+            const float invstd = invstd_in[c];
+            mu[e] = ref[e];
+            gm[e] = train ? (float)(a / dn) : 0.f;
+            kk[e] = train ? (float)(b * (double)invstd * (double)invstd / dn) : 0.f;
+            if (writer) {
+                if (d_weight) d_weight[c] = (float)(b * (double)invstd);
+                if (d_bias) d_bias[c] = (float)a;
+            }
+        }
+    }
+    if (blockIdx.x == 0) {  // leave the other parity's block clean for the next call, then flip
+        double *other = reinterpret_cast<double *>(ws + kBnFusedOff + 8) + (par ^ 1) * 2 * kBnMaxPlanes;
+        for (int i = tid; i < 2 * kBnMaxPlanes; i += nthr) other[i] = 0.0;
+        if (tid == 0) {
+            reinterpret_cast<unsigned *>(hdr)[2 + (par ^ 1)] = 0u;
+            hdr[0] = par ^ 1;
+        }
+    }
+    if (out == nullptr) return;
+    // ---- apply over the same slab
+    auto apply_row = [&](float (&v)[VEC], const float (&d)[VEC]) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const float y = fmaf(v[e], sc[e], sh[e]);
+            if (BWD) {
+                const float dm = y > 0.f ? d[e] : d[e] * leakiness;
+                v[e] = (dm - gm[e] - (v[e] - mu[e]) * kk[e]) * sc[e];
+            } else {
+                v[e] = y > 0.f ? y : y * leakiness;
+            }
+        }
+    };
+    r = r0 + threadIdx.y;
+    for (; r + 3 * stride < r1; r += 4 * stride) {
+        float v[4][VEC], d[4][VEC], o[4][VEC];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            Vec<VEC>::get(x + (r + q * stride) * ld_x + c0, v[q]);
+            if (BWD) Vec<VEC>::get(dout + (r + q * stride) * ld_dout + c0, d[q]);
+            if (BWD && accumulate) Vec<VEC>::get(out + (r + q * stride) * ld_out + c0, o[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            apply_row(v[q], d[q]);
+            if (BWD && accumulate) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) v[q][e] = __fadd_rn(v[q][e], o[q][e]);
+            }
+            Vec<VEC>::put(out + (r + q * stride) * ld_out + c0, v[q]);
+        }
+    }
+    for (; r < r1; r += stride) {
+        float v[VEC], d[VEC];
+        Vec<VEC>::get(x + r * ld_x + c0, v);
+        if (BWD) Vec<VEC>::get(dout + r * ld_dout + c0, d);
+        apply_row(v, d);
+        if (BWD && accumulate) {
+            float o[VEC];
+            Vec<VEC>::get(out + r * ld_out + c0, o);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v[e] = __fadd_rn(v[e], o[e]);
+        }
+        Vec<VEC>::put(out + r * ld_out + c0, v);
+    }
+}
+
+// blocks of the cooperative launch: enough rows per thread to amortise the barrier, never more than can be co-resident
+template <int VEC, bool BWD>
+static int launch_bn_fused(const BnShapeArgs &A, cudaStream_t s);
+
 struct BnShape {
     int vec;
     dim3 block;
@@ -235,6 +430,40 @@ static BnShape bn_shape(int64_t n, int planes, bool vec_ok) {
     return s;
 }
 static bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+static bool bn_fused_enabled() {  // MOPA_SCN_NO_BNFUSED=1: the two-kernel path (A/B measurements; read per call)
+    const char *e = getenv("MOPA_SCN_NO_BNFUSED");
+    return !(e && e[0] == '1');
+}
+template <int VEC, bool BWD>
+static int launch_bn_fused(const BnShapeArgs &A, cudaStream_t s) {
+    const int tx = A.planes / VEC;
+    int ty = 256 / tx;
+    if (ty < 1) ty = 1;
+    if (ty > 64) ty = 64;
+    const size_t smem = (size_t)ty * 2 * A.planes * 4;
+    auto kern = k_bn_fused<VEC, BWD>;
+    static int max_blocks = 0;  // per instantiation
+    if (max_blocks == 0) {
+        int dev = 0, sms = 0, occ = 0;
+        MOPA_CUDA(cudaGetDevice(&dev));
+        MOPA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        MOPA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 16 * 1024));
+        if (occ > 2) occ = 2;
+        MOPA_CHECK(occ >= 1 && sms >= 1, "BatchNormalization: the fused kernel does not fit on this device");
+        max_blocks = occ * sms;
+    }
+    int64_t want = ceil_div(A.n, (int64_t)ty * 8);  // >= 8 rows per thread
+    if (want < 1) want = 1;
+    if (want > max_blocks) want = max_blocks;
+    BnShapeArgs a = A;
+    void *args[] = {&a.x, &a.ld_x, &a.dout, &a.ld_dout, &a.out, &a.ld_out, &a.n, &a.planes, &a.ws, &a.mean_in, &a.invstd_in,
+                    &a.weight, &a.bias, &a.leakiness, &a.train, &a.eps, &a.momentum, &a.save_mean, &a.save_invstd,
+                    &a.running_mean, &a.running_var, &a.d_weight, &a.d_bias, &a.accumulate};
+    MOPA_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)want), dim3(tx, ty), args, smem, s));
+    MOPA_LAUNCHED();
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------ IO layers
 // InputLayer mode 4: out[v][c] = sum over the voxel's rows, ascending, of (1/n_v) * in[row][c]  (multiply, then add)
@@ -310,6 +539,13 @@ int bn_forward(const float *in, int64_t ld_in, float *out, int64_t ld_out, float
     MOPA_CHECK(sh.block.x * sh.block.y <= 256, "BatchNormalization: unaligned features with more than 256 planes");
     float *ws = reinterpret_cast<float *>(workspace);
     const int prof = prof_begin(40, nullptr, planes, planes, n_active, s);
+    if (train && sh.vec == 4 && bn_fused_enabled()) {
+        const BnShapeArgs A{in, ld_in, nullptr, 0, out, ld_out, n_active, planes, ws, nullptr, nullptr, weight, bias, leakiness,
+                            1, eps, momentum, save_mean, save_invstd, running_mean, running_var, nullptr, nullptr, 0};
+        const int rc = launch_bn_fused<4, false>(A, s);
+        prof_end(prof, s);
+        return rc;
+    }
     if (train) {
         if (sh.vec == 4)
             k_bn_stats<4, false><<<sh.grid, sh.block, sh.smem, s>>>(in, ld_in, nullptr, 0, n_active, planes, ws, nullptr,
@@ -352,6 +588,13 @@ int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, con
     MOPA_CHECK(sh.block.x * sh.block.y <= 256, "BatchNormalization: unaligned features with more than 256 planes");
     float *ws = reinterpret_cast<float *>(workspace);
     const int prof = prof_begin(50, nullptr, planes, planes, n_active, s);
+    if (sh.vec == 4 && bn_fused_enabled()) {
+        const BnShapeArgs A{in, ld_in, d_out, ld_dout, d_in, ld_din, n_active, planes, ws, save_mean, save_invstd, weight, bias,
+                            leakiness, train, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, d_weight, d_bias, accumulate};
+        const int rc = launch_bn_fused<4, true>(A, s);
+        prof_end(prof, s);
+        return rc;
+    }
     if (sh.vec == 4)
         k_bn_stats<4, true><<<sh.grid, sh.block, sh.smem, s>>>(in, ld_in, d_out, ld_dout, n_active, planes, ws, save_mean,
                                                                save_invstd, weight, bias, leakiness, train, 0.f, 0.f,

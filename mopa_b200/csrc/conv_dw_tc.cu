@@ -38,6 +38,7 @@ constexpr int kDwTcTile = 32;    // rules per stage
 constexpr int kDwTcSub = 512;    // rows looked up per producer pass (4 per thread)
 constexpr int kDwTcList = 1024;  // pending-rule ring (entries); holds < 32 + 512
 constexpr int kDwTcMaxStages = 12;
+constexpr int kDwTcLook = 3;    // producer passes of table lookups in flight
 
 struct DwTcPlan {
     int centre;  // 13 for a submanifold table, -1 otherwise
@@ -193,19 +194,19 @@ __global__ void __launch_bounds__(kDwTcThreads)
             if (++st == stages) { st = 0; ph ^= 1; }
         };
 
-        int v[4], vn[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int64_t row = r_begin + q * 128 + tid;
-            vn[q] = row < r_end ? gather_lookup(gt, k, row) : -1;
-        }
-        for (int64_t sub = r_begin; sub < r_end; sub += kDwTcSub) {
+        // table lookups run kDwTcLook passes ahead of their use (register ring with static indices): a pass is shorter
+        // than an L2/HBM round trip
+        int vq[kDwTcLook][4];
+        auto look = [&](int64_t sub, int (&dst)[4]) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                v[q] = vn[q];
-                const int64_t row = sub + kDwTcSub + q * 128 + tid;
-                vn[q] = row < r_end ? gather_lookup(gt, k, row) : -1;
+                const int64_t row = sub + q * 128 + tid;
+                dst[q] = row < r_end ? gather_lookup(gt, k, row) : -1;
             }
+        };
+#pragma unroll
+        for (int u = 0; u < kDwTcLook; ++u) look(r_begin + (int64_t)u * kDwTcSub, vq[u]);
+        auto pass = [&](int64_t sub, const int (&v)[4]) {
             uint32_t m[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -239,6 +240,19 @@ __global__ void __launch_bounds__(kDwTcThreads)
             while (tail - head >= kDwTcTile) {
                 emit(kDwTcTile, 0u);
                 head += kDwTcTile;
+            }
+        };
+        for (int64_t sub0 = r_begin; sub0 < r_end; sub0 += (int64_t)kDwTcLook * kDwTcSub) {
+#pragma unroll
+            for (int u = 0; u < kDwTcLook; ++u) {
+                const int64_t sub = sub0 + (int64_t)u * kDwTcSub;
+                if (sub < r_end) {  // uniform over the producers
+                    int v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = vq[u][q];
+                    look(sub + (int64_t)kDwTcLook * kDwTcSub, vq[u]);
+                    pass(sub, v);
+                }
             }
         }
         emit(tail - head, 1u);  // always: carries the "last" flag (and initialises the accumulator of an empty item)
@@ -301,13 +315,14 @@ __global__ void __launch_bounds__(kDwTcThreads)
     if (warp == 4) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// d_weight[k][e] = sum of the item slices of offset k, in item order
+// d_weight[k][e] = sum of the item slices of offset k. grid (element blocks of 32, offsets), block (32 elements, 8 slice
+// groups): thread (x, y) adds slices y, y + 8, ... in order, the 8 partial sums are combined in y order: a fixed summation
+// tree (deterministic, no float atomics) with 8x shorter load chains than one thread per element.
 __global__ void __launch_bounds__(256) k_dw_tc_reduce(const float *__restrict__ partial, int64_t mat, DwTcPlan plan,
-                                                      float *__restrict__ dw, int64_t total) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int k = (int)(idx / mat);
-    const int64_t e = idx - (int64_t)k * mat;
+                                                      float *__restrict__ dw) {
+    __shared__ float red[8][33];
+    const int k = blockIdx.y;
+    const int64_t e = (int64_t)blockIdx.x * 32 + threadIdx.x;
     int beg, cnt;
     if (plan.centre >= 0) {
         if (k == plan.centre) { beg = 0; cnt = plan.n_c; }
@@ -316,17 +331,24 @@ __global__ void __launch_bounds__(256) k_dw_tc_reduce(const float *__restrict__ 
         beg = k * plan.n_o;
         cnt = plan.n_o;
     }
-    const float *p = partial + (int64_t)beg * mat + e;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int c = 0;
-    for (; c + 3 < cnt; c += 4) {
-        s0 += p[(int64_t)c * mat];
-        s1 += p[(int64_t)(c + 1) * mat];
-        s2 += p[(int64_t)(c + 2) * mat];
-        s3 += p[(int64_t)(c + 3) * mat];
+    float s0 = 0.f, s1 = 0.f;
+    if (e < mat) {
+        const float *p = partial + (int64_t)beg * mat + e;
+        int c = threadIdx.y;
+        for (; c + 8 < cnt; c += 16) {
+            s0 += p[(int64_t)c * mat];
+            s1 += p[(int64_t)(c + 8) * mat];
+        }
+        if (c < cnt) s0 += p[(int64_t)c * mat];
     }
-    for (; c < cnt; ++c) s0 += p[(int64_t)c * mat];
-    dw[idx] = (s0 + s1) + (s2 + s3);
+    red[threadIdx.y][threadIdx.x] = s0 + s1;
+    __syncthreads();
+    if (threadIdx.y == 0 && e < mat) {
+        float s = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x];
+        dw[(int64_t)k * mat + e] = s;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -368,8 +390,8 @@ int conv_dweight_tc(const Gather &gt, const float *in, int64_t ld_in, const floa
     k_dw_tc<<<(unsigned)plan.items, kDwTcThreads, smem, s>>>(gt, in, ld_in, dout, ld_dout, n_in, n_out, swap, plan, stages,
                                                            partial);
     MOPA_LAUNCHED();
-    const int64_t mat = (int64_t)n_in * n_out, total = (int64_t)gt.volume * mat;
-    k_dw_tc_reduce<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(partial, mat, plan, dw, total);
+    const int64_t mat = (int64_t)n_in * n_out;
+    k_dw_tc_reduce<<<dim3((unsigned)ceil_div(mat, 32), gt.volume), dim3(32, 8), 0, s>>>(partial, mat, plan, dw);
     MOPA_LAUNCHED();
     return 0;
 }

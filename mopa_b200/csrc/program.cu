@@ -12,6 +12,8 @@
 #include <map>
 #include <mutex>
 
+#include <stdlib.h>
+
 #include "geometry.cuh"
 #include "mopa_scn.h"
 
@@ -50,6 +52,28 @@ static int geom_stream(int device, cudaStream_t *out) {
     return 0;
 }
 
+// d_weight kernels run on a second (lowest-priority) stream, forked from the main stream once the op's output gradient
+// is complete: they depend on nothing the rest of the backward pass produces, and fill the SMs the last (partial) wave
+// of the d_input kernels leaves idle. MOPA_SCN_NO_DW_OVERLAP=1 keeps everything on one stream (A/B measurements).
+static std::map<int, cudaStream_t> g_dw_streams;
+static int dw_stream(int device, cudaStream_t *out) {
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    auto it = g_dw_streams.find(device);
+    if (it == g_dw_streams.end()) {
+        int lo = 0, hi = 0;
+        MOPA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        cudaStream_t s;
+        MOPA_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, lo));
+        it = g_dw_streams.emplace(device, s).first;
+    }
+    *out = it->second;
+    return 0;
+}
+static bool dw_overlap_enabled() {
+    const char *e = getenv("MOPA_SCN_NO_DW_OVERLAP");
+    return !(e && e[0] == '1');
+}
+
 }  // namespace mopa
 
 struct mopa_scn_program {
@@ -58,6 +82,8 @@ struct mopa_scn_program {
     int in_planes = 0, in_buf = 0, out_buf = 0, n_levels = 1, device = 0;
     int64_t spatial = 0;
     void *bn_ws = nullptr;  // persistent, zero-initialised (the BN kernels leave it zeroed)
+    std::vector<cudaEvent_t> fork_events;  // one per op (main stream -> d_weight stream), created on first use
+    cudaEvent_t join_event = nullptr;
 };
 
 namespace mopa {
@@ -162,6 +188,9 @@ mopa_scn_program *mopa_scn_Program_new(const int32_t *ops, int n_ops, const int3
 void mopa_scn_Program_delete(mopa_scn_program *p) {
     if (!p) return;
     if (p->bn_ws) cudaFree(p->bn_ws);
+    for (cudaEvent_t e : p->fork_events)
+        if (e) cudaEventDestroy(e);
+    if (p->join_event) cudaEventDestroy(p->join_event);
     delete p;
 }
 
@@ -257,6 +286,13 @@ int mopa_scn_Program_backward(mopa_scn_program *p, mopa_scn_metadata *m, const v
         for (size_t c = 0; c < nb; ++c)
             if (p->bufs[c].parent == b) written[c] = 1;
     };
+    cudaStream_t s2 = s;  // stream of the d_weight kernels
+    bool forked = false;
+    if (dw_overlap_enabled()) {
+        MOPA_TRY(dw_stream(m->device, &s2));
+        if (p->fork_events.size() != p->ops.size()) p->fork_events.assign(p->ops.size(), nullptr);
+        if (!p->join_event) MOPA_CUDA(cudaEventCreateWithFlags(&p->join_event, cudaEventDisableTiming));
+    }
     BufView g_last = view(L, grad_arena, p->out_buf);
     MOPA_TRY(mopa_scn_OutputLayer_updateGradInput(m, g_last.ptr, g_last.ld, d_out, ld_dout, p->bufs[p->out_buf].channels, s));
     mark(p->out_buf);
@@ -285,6 +321,17 @@ int mopa_scn_Program_backward(mopa_scn_program *p, mopa_scn_metadata *m, const v
                                  m->levels[o.level_in].V, o.n_in, p->bn_ws, accumulate, s));
         } else {
             const float *w = (const float *)params[o.param];
+            // d_weight first: it is forked to its own stream and overlaps the d_input kernel of the same op
+            if (param_grads[o.param]) {
+                if (s2 != s) {  // dy is complete on the main stream here; nothing later in this pass writes it again
+                    if (!p->fork_events[i]) MOPA_CUDA(cudaEventCreateWithFlags(&p->fork_events[i], cudaEventDisableTiming));
+                    MOPA_CUDA(cudaEventRecord(p->fork_events[i], s));
+                    MOPA_CUDA(cudaStreamWaitEvent(s2, p->fork_events[i], 0));
+                    forked = true;
+                }
+                MOPA_TRY(conv_dweight(op_gather(o, m, false), x.ptr, x.ld, dy.ptr, dy.ld, (float *)param_grads[o.param],
+                                      o.n_in, o.n_out, precision, dw_ws, L.dw_bytes, s2));
+            }
             if (need_din) {
                 const float *pk = nullptr;
                 if (conv_uses_packed(o.n_out, o.n_in)) {
@@ -296,11 +343,12 @@ int mopa_scn_Program_backward(mopa_scn_program *p, mopa_scn_metadata *m, const v
                 MOPA_TRY(conv_apply(g, dy.ptr, dy.ld, dx.ptr, dx.ld, w, pk, o.n_in, o.n_out, 1, o.type == OP_SUBM ? 1 : 0,
                                     precision, s));
             }
-            if (param_grads[o.param])
-                MOPA_TRY(conv_dweight(op_gather(o, m, false), x.ptr, x.ld, dy.ptr, dy.ld, (float *)param_grads[o.param],
-                                      o.n_in, o.n_out, precision, dw_ws, L.dw_bytes, s));
         }
         if (need_din) mark(o.in);
+    }
+    if (forked) {  // the caller's stream owns every buffer again only after the d_weight stream has drained
+        MOPA_CUDA(cudaEventRecord(p->join_event, s2));
+        MOPA_CUDA(cudaStreamWaitEvent(s, p->join_event, 0));
     }
     if (d_feats) {
         BufView g0 = view(L, grad_arena, p->in_buf);

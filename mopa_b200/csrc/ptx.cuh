@@ -150,6 +150,12 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatil
 __device__ __forceinline__ void cp_async16_s(uint32_t dst, const void *gmem_src, int src_bytes) {  // src_bytes 0 => zero fill
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(src_bytes));
 }
+// predicated form: compiles to one @P LDGSTS (an `if` around the asm costs a branch + reconvergence pair per site)
+__device__ __forceinline__ void cp_async16_pred_s(uint32_t dst, const void *gmem_src, int src_bytes, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(dst),
+        "l"(gmem_src), "r"(src_bytes), "r"((int)pred));
+}
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc_s(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }

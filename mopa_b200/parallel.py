@@ -2,9 +2,10 @@
 
 One process per GPU; every rank holds a full UNetSCN replica and its own scans (a scan is never split); BatchNorm
 statistics stay per rank, as in the reference's single-GPU batch of 8. The only exchange is one gradient all-reduce
-(mean) per optimizer step over NCCL/NVLink: all gradients live in ONE flat fp32 bucket (~10.8 MB for UNetSCN) that
-autograd accumulates into directly, so the collective needs no packing copies and MoPA's two backward() calls per step
-(train_xmuda_mopa.py:417-418,578-579) reduce once.
+(mean) per optimizer step over NCCL/NVLink: all gradients are packed into ONE flat fp32 bucket (~10.8 MB for UNetSCN)
+by a single multi-tensor copy, so the collective is one call and MoPA's two backward() calls per step
+(train_xmuda_mopa.py:417-418,578-579) reduce once. (Pointing .grad at bucket slices BEFORE backward made autograd run
+one small add kernel per parameter, 78 launches per step; with .grad = None autograd just keeps the produced tensor.)
 """
 import torch
 import torch.distributed as dist
@@ -18,7 +19,9 @@ def shard_scans(n_scans, rank, world_size):
 
 
 class FlatGradBucket:
-    """Points every parameter's .grad at a slice of one flat buffer; all_reduce() averages it across ranks in place."""
+    """One flat buffer with a slice per parameter. zero() drops the gradients (no kernel); pack() copies the gradients
+    autograd produced into their slices with one multi-tensor copy and points .grad at the slices; all_reduce() packs
+    and averages the buffer across ranks in place."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
@@ -27,17 +30,35 @@ class FlatGradBucket:
         dev, dtype = self.params[0].device, self.params[0].dtype
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=dtype, device=dev)
+        self.views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        self.zero()
 
     def zero(self):
-        self.flat.zero_()
+        for p in self.params:
+            p.grad = None
+
+    def pack(self):
+        src, dst = [], []
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                v.zero_()  # parameter not reached by this step's backward passes
+            elif g.data_ptr() != v.data_ptr():
+                src.append(g.detach())
+                dst.append(v)
+        if src:
+            torch._foreach_copy_(dst, src)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def all_reduce(self, async_op=False):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return None
+            return None  # single process: the gradients stay where autograd put them
+        self.pack()
         if dist.get_backend() == "nccl":
             return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, async_op=async_op)
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)  # gloo has no AVG

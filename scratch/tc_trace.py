@@ -1,38 +1,45 @@
-"""Timeline of CTA 0 of one k_conv_tc launch (MOPA_TC_DBG=32): python scratch/tc_trace.py CIN COUT ROWS"""
+"""Timeline of one mid-grid CTA of a k_conv_tc launch (MOPA_TC_DBG=32): python scratch/tc_trace.py CIN COUT [scans]"""
 import ctypes, os, sys
 os.environ["MOPA_TC_DBG"] = str(32 | int(os.environ.get("EXTRA_DBG", "0")))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import mopa_b200.scn as scn
-from mopa_b200 import _lib
-from tests.helpers import small_batch
-cin, cout = int(sys.argv[1]), int(sys.argv[2])
-naz = int(sys.argv[3]) if len(sys.argv) > 3 else 300
-coords, _ = small_batch(4, naz, 0)
-feats = torch.randn(coords.shape[0], cin).cuda()
-x = scn.InputLayer(3, 4096, mode=4)([torch.from_numpy(coords), feats])
-conv = scn.SubmanifoldConvolution(3, cin, cout, 3, False).cuda()
-for _ in range(3):
-    y = conv(x)
-torch.cuda.synchronize()
+from mopa_b200 import _lib, synth
+scn.set_precision("tf32")
 lib = _lib.load()
-buf = np.zeros((8, 512), np.int64)
 lib.mopa_scn_debug_tc_trace.argtypes = [ctypes.c_void_p]
-print("rc", lib.mopa_scn_debug_tc_trace(buf.ctypes.data), "rows", x.features.shape[0])
-n = 27 * ((cin + 31) // 32)
-t0 = buf[buf > 0].min()
-b = buf - t0
-names = ["g:loop top", "g:landed", "g:a_empty ok", "g:arrived", "i:step top", "i:b_full ok", "i:a_full ok", "i:committed"]
-print("step " + " ".join("%12s" % s for s in names))
-for i in list(range(0, min(n, 14))) + list(range(max(14, n - 4), n)):
-    print("%4d " % i + " ".join("%12d" % b[r, i] for r in range(8)))
-d = np.diff(b[3, :n])
-print("gather warp0 arrive-to-arrive cycles: mean %.0f median %.0f" % (d.mean(), np.median(d)))
-print("mean phase cycles per step: issue->landed %.0f, landed->a_empty %.0f, a_empty->arrived %.0f" % (
-    (b[1, :n] - b[0, :n]).mean(), (b[2, :n] - b[1, :n]).mean(), (b[3, :n] - b[2, :n]).mean()))
-print("issuer: top->b_full %.0f, b_full->a_full(t0) %.0f, a_full->commit %.0f" % (
-    (b[5, :n] - b[4, :n]).mean(), (b[6, :n] - b[5, :n]).mean(), (b[7, :n] - b[6, :n]).mean()))
-
-if int(os.environ.get("EXTRA_DBG", "0")) & 64:
-    print("issuer fine (cycles): a_full(t0)->fenced %.0f, fenced->4 MMAs issued %.0f, ->commit(a_empty t0) %.0f, ->tile1 done %.0f, ->commit(b) %.0f" % (
-        (b[0, :n] - b[6, :n]).mean(), (b[1, :n] - b[0, :n]).mean(), (b[2, :n] - b[1, :n]).mean(), (b[3, :n] - b[2, :n]).mean(), (b[7, :n] - b[3, :n]).mean()))
+args = [int(a) for a in sys.argv[1:]]
+nscan = 8
+coords, _ = synth.make_batch(nscan, "nuscenes", 0)
+for cin, cout in zip(args[0::2], args[1::2]):
+    feats = torch.randn(coords.shape[0], cin).cuda()
+    x = scn.InputLayer(3, 4096, mode=4)([torch.from_numpy(coords), feats])
+    conv = scn.SubmanifoldConvolution(3, cin, cout, 3, False).cuda()
+    with torch.no_grad():
+        for _ in range(3):
+            y = conv(x)
+    torch.cuda.synchronize()
+    buf = np.zeros((8, 512), np.int64)
+    lib.mopa_scn_debug_tc_trace(buf.ctypes.data)   # clear
+    with torch.no_grad():
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(); y = conv(x); t1.record()
+    torch.cuda.synchronize()
+    print("== %d->%d rows %d kernel+pack %.1f us" % (cin, cout, x.features.shape[0], 1e3 * t0.elapsed_time(t1)))
+    lib.mopa_scn_debug_tc_trace(buf.ctypes.data)
+    n = 27 * ((cin + 31) // 32)
+    g_top, g_emp, g_arr, i_top, i_full, i_com = (buf[r, :n].astype(np.float64) for r in (0, 1, 2, 4, 5, 6))
+    base = g_top[0]
+    print("step   g:top  g:a_empty  g:arrived | i:top  i:a_full  i:committed   (cycles from first step)")
+    for i in list(range(0, min(n, 12))) + list(range(max(12, n - 3), n)):
+        print("%4d %7d %9d %9d | %7d %8d %8d" % (i, g_top[i] - base, g_emp[i] - base, g_arr[i] - base, i_top[i] - base, i_full[i] - base, i_com[i] - base))
+    d = np.diff(g_arr)
+    print("gather warp 0: arrive-to-arrive mean %.0f median %.0f cycles; wait for a_empty mean %.0f; issue (a_empty -> arrive) mean %.0f" % (
+        d.mean(), np.median(d), (g_emp - g_top).mean(), (g_arr - g_emp).mean()))
+    print("issuer: wait for a_full mean %.0f; a_full -> committed mean %.0f; step-to-step mean %.0f" % (
+        (i_full - i_top).mean(), (i_com - i_full).mean(), np.diff(i_top).mean()))
+    print("gather arrive -> issuer sees a_full: mean %.0f median %.0f (includes the data landing)" % ((i_full - g_arr).mean(), np.median(i_full - g_arr)))
+    sa = int(os.environ.get("TRACE_RING", "3"))
+    if n > sa:
+        lat = g_emp[sa:] - i_com[:-sa]
+        print("issuer commit of step s -> gather acquires the stage for step s+%d: mean %.0f median %.0f min %.0f" % (sa, lat.mean(), np.median(lat), lat.min()))

@@ -35,11 +35,12 @@ def _worker(rank, world, port, out):
         parallel.broadcast_parameters(net)
         w0 = torch.cat([p.detach().flatten() for p in net.parameters()])
         bucket = parallel.FlatGradBucket(net.parameters())
-        # two backward() calls per step (train_xmuda_mopa.py:417-418,578-579) accumulate into the flat bucket, one reduce
+        # two backward() calls per step (train_xmuda_mopa.py:417-418,578-579) accumulate locally, one pack + one reduce
         x = torch.full((5, 4), float(rank + 1))
         bucket.zero()
         net(x).sum().backward()
         net(2 * x).sum().backward()
+        bucket.pack()
         local = bucket.flat.clone()
         bucket.all_reduce()
         gathered = [torch.zeros_like(local) for _ in range(world)]
