@@ -37,6 +37,8 @@ def build(force=False, verbose=False):
                "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+        for d in os.environ.get("MOPA_BUILD_DEFS", "").split():  # e.g. MOPA_TC_TRACE (debug timeline in conv_tc.cu)
+            cmd.insert(1, "-D" + d)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

@@ -35,7 +35,7 @@
 namespace mopa {
 
 constexpr int kTcTM = 256;            // output rows per CTA (two M = 128 tiles)
-constexpr int kTcThreads = 10 * 32;
+constexpr int kTcThreads = 11 * 32;  // 8 gather warps, weight producer, two MMA issuers
 constexpr int kTcChunk = 32;          // input channels per pipeline step (one 128-byte swizzle row)
 constexpr int kTcAStage = 128 * 128;  // bytes: 128 rows x 128 bytes
 constexpr int kTcMaxSA = 12, kTcMaxSB = 8;
@@ -70,6 +70,15 @@ __global__ void __launch_bounds__(256) k_pack_weights_tc(const float *__restrict
     if (ci < c_in) v = transpose ? w[((int64_t)ks * n_in0 + co) * n_out0 + ci] : w[((int64_t)ks * n_in0 + ci) * n_out0 + co];
     packed[idx] = __uint_as_float(to_tf32(v));
 }
+
+#ifdef MOPA_TC_TRACE
+// debug timeline (build with -DMOPA_TC_TRACE, run scratch/tc_trace.py): clock64 stamps of one mid-grid CTA, rows: 0 gather
+// step top, 1 a_empty acquired, 2 copies issued + arrive, 4 issuer before a_full wait, 5 a_full seen, 6 MMAs + commit issued
+__device__ long long g_tc_trace[8][512];
+#define TC_STAMP(cond, row, idx) do { if ((cond) && (idx) < 512) g_tc_trace[row][idx] = clock64(); } while (0)
+#else
+#define TC_STAMP(cond, row, idx) do { } while (0)
+#endif
 
 struct TcSmem {  // byte offsets inside the dynamic shared memory block (base aligned to 1024)
     int a, b, mask, bars, total;
@@ -107,8 +116,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 
     if (tid == 0) {
         for (int i = 0; i < SA; ++i) { mbar_init(a_full + i, 128); mbar_init(a_empty + i, 1); }
-        for (int i = 0; i < SB; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-        mbar_init(d_full, 1);
+        for (int i = 0; i < SB; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, n_mt); }
+        mbar_init(d_full, n_mt);
         mbar_fence_init();
     }
     if (warp == 9) tmem_alloc(tmem_ptr, tmem_cols);
@@ -123,7 +132,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     if (warp < 8) {
         // ================================================================= gather warps
         // warps 0-3 feed M tile 0, warps 4-7 M tile 1; warp w owns tile rows [32 (w & 3), +32) = TMEM lane quarter w & 3
-        const int mt = warp >> 2, wq = warp & 3, grp = lane >> 3, c = lane & 7;  // lane group -> row, lane & 7 -> 16-byte piece
+        const int mt = warp >> 2, wq = warp & 3;
         const bool live = mt < n_mt;
         const int64_t row = row0 + 128 * mt + 32 * wq + lane;
         const bool row_ok = live && row < gt.n_out;
@@ -147,52 +156,60 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         int nq[kTcLook];
 #pragma unroll
         for (int u = 0; u < kTcLook; ++u) nq[u] = look(u);
-        // Per step (offset k, 32-channel chunk) a warp (lane = row) does: one ballot, then up to 8 passes of 4 rows x 8
-        // lanes (16-byte pieces): rows with a rule get their 128 bytes by cp.async; rows the warp wrote in the stage's
-        // previous use and does not rewrite are zero-filled through the same async path, so a stage is zero outside its
-        // live rules. Which rows were written last time lives in registers (lane s keeps the record of stage s): no shared
-        // memory lists, no __syncwarp. (The first version kept compacted row lists in shared memory and spent ~220
-        // instructions per step; ncu showed the gather warps issue-latency bound on that bookkeeping.)
+        // Per step (offset k, 32-channel chunk) a warp (lane = row for the lookup) does one ballot and then NP passes of
+        // 32 / LPR rows x LPR lanes (one 16-byte piece per lane): rows with a rule get their bytes by cp.async; rows the
+        // warp wrote in the stage's previous use and does not rewrite are zero-filled through the same instruction
+        // (ignore-src operand), so a stage is zero outside its live rules. Which rows were written last time lives in
+        // registers (lane s keeps the record of stage s): no shared-memory lists, no __syncwarp, no branches inside a
+        // pass. Everything that does not change per step (row of each pass, its bit, its swizzled offset) is hoisted.
+        // History: the first version kept compacted row lists in shared memory (~220 instructions per step), the second
+        // used the src-size form of cp.async (~370 SASS instructions per step after ptxas expanded it); a device-side
+        // timeline (scratch/tc_trace.py) showed the gather warps spend ~1800 cycles per step ISSUING and ~80 waiting.
         uint32_t oldm = 0, oldp = 0;
-        const bool narrow = c_in == 16;  // 64-byte rows: 4 lanes per row, 8 rows per pass
-        const int c4 = lane & 3, grp8 = lane >> 2;
+        int tstep = 0;  // trace builds only
+        const int LPR = c_in == 16 ? 4 : 8;      // lanes per row (64-byte rows need 4)
+        const int NP = LPR;                      // passes per step: 32 rows / (32 / LPR rows per pass)
+        const int cl = lane & (LPR - 1);         // this lane's 16-byte piece
+        const int rl = lane / LPR;               // row inside a pass
+        uint32_t bit[8], doff[8];
+        int rj[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = (j * (32 / LPR) + rl) & 31;
+            rj[j] = r;
+            bit[j] = j < NP ? 1u << r : 0u;
+            doff[j] = (uint32_t)r * 128 + (uint32_t)((cl ^ (r & 7)) << 4);
+        }
+        const char *in_c = reinterpret_cast<const char *>(in) + 16 * cl;
+        const uint32_t ldb = (uint32_t)ld_in * 4;  // row pitch in bytes (feature matrices are far below 4 GB)
         auto step = [&](const int nv) {
             const uint32_t m_new = __ballot_sync(0xffffffffu, nv >= 0);
-            const float *src = in + 4 * (narrow ? c4 : c);
-            for (int ch = 0; ch < nchunk; ++ch, src += kTcChunk) {
+            const char *rp[8];  // source row of each pass (row 0 where there is no rule: never read, must be mapped)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int srow = __shfl_sync(0xffffffffu, nv, rj[j]);
+                rp[j] = in_c + (uint64_t)(uint32_t)max(srow, 0) * (uint64_t)ldb;
+            }
+            for (int ch = 0; ch < nchunk; ++ch) {
                 const uint32_t pieces = (uint32_t)min(kTcChunk, c_in - ch * kTcChunk) / 4;  // 16-byte pieces per row
+                TC_STAMP(warp == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 0, tstep);
                 mbar_wait_s(empty0_a + 8 * st, ph);
+                TC_STAMP(warp == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 1, tstep);
                 const uint32_t m_old = __shfl_sync(0xffffffffu, oldm, st), p_old = __shfl_sync(0xffffffffu, oldp, st);
-                const uint32_t need = m_new | m_old;
+                const uint32_t a_new = (uint32_t)cl < pieces ? m_new : 0u;  // rows this lane copies / may have to clear
+                const uint32_t a_old = (uint32_t)cl < p_old ? m_old : 0u;
                 const uint32_t tile_a = tile0_a + st * kTcAStage;
-                // all shuffles first (independent, pipelined), then predicated copies: no branches inside the step, so the
-                // in-order warp never waits on a shuffle result it does not need yet
-                if (narrow) {
-                    int srow[4];
+                const int cho = ch * (kTcChunk * 4);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) srow[j] = __shfl_sync(0xffffffffu, nv, 8 * j + grp8);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int r = 8 * j + grp8;
-                        const bool is_new = (m_new >> r) & 1u;
-                        cp_async16_pred_s(tile_a + r * 128 + ((c4 ^ (r & 7)) << 4), is_new ? src + (int64_t)srow[j] * ld_in : in,
-                                          is_new ? 16 : 0, (need >> r) & 1u);
-                    }
-                } else {
-                    int srow[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) srow[j] = __shfl_sync(0xffffffffu, nv, 4 * j + grp);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int r = 4 * j + grp;
-                        const bool is_new = ((m_new >> r) & 1u) && (uint32_t)c < pieces;
-                        cp_async16_pred_s(tile_a + r * 128 + ((c ^ (r & 7)) << 4), is_new ? src + (int64_t)srow[j] * ld_in : in,
-                                          is_new ? 16 : 0, is_new || (((m_old >> r) & 1u) && (uint32_t)c < p_old));
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t is_new = a_new & bit[j];
+                    cp_async16_zfill_pred_s(tile_a + doff[j], rp[j] + cho, is_new | (a_old & bit[j]), is_new == 0u);
                 }
                 // every lane: "my copies of this step have landed" arrives on the stage's barrier asynchronously (128
                 // arrivals complete it); the warp never waits for data, so all stages of the ring can be in flight
                 cp_async_mbar_arrive_noinc_s(full0_a + 8 * st);
+                TC_STAMP(warp == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 2, tstep);
+                ++tstep;
                 if (lane == st) { oldm = m_new; oldp = pieces; }
                 st += TPC;
                 if (st >= SA) { st -= SA; ph ^= 1; }
@@ -242,45 +259,46 @@ __global__ void __launch_bounds__(kTcThreads, 2)
                 if (++st == SB) { st = 0; ph ^= 1; }
             }
         }
-    } else {
-        // ================================================================= MMA issuer
+    } else if (warp - 9 < n_mt) {
+        // ================================================================= MMA issuers: warp 9 -> M tile 0, warp 10 -> M tile 1
+        // One issuer per tile: a single issuer served the two tiles in turn, so a late stage of one tile held back the
+        // other (the timeline showed ~450 cycles per tile step in this warp, two tiles back to back per step).
         // The whole warp runs the (warp-uniform) loops and waits; one elected lane executes the tcgen05 instructions. Keeping
         // the control flow uniform keeps the descriptors in uniform registers (issuing from an `if (lane == 0)` branch cost
-        // ~130 cycles of R2UR traffic per MMA and made this warp the bottleneck of the whole CTA).
-        {
-            const uint32_t idesc = umma_idesc_tf32(NT);
-            const uint64_t desc_hi = umma_desc_sw128(0);  // everything but the start address
-            int st = 0, ph = 0, stb = 0, phb = 0;
-            for (int k = 0; k < K; ++k) {
-                for (int ch = 0; ch < nchunk; ++ch) {
-                    mbar_wait(b_full + stb, phb);
-                    const int nk = min(kTcChunk, c_in - ch * kTcChunk) / 8;  // MMAs (K = 8 each) in this chunk
-                    const uint64_t b_desc = desc_hi | (uint64_t)((smem_u32(sB + (size_t)stb * NT * 128) & 0x3FFFFu) >> 4);
-                    for (int mt = 0; mt < TPC; ++mt) {  // stage order: step TPC j + mt, also when only tile 0 is live
-                        if (mt < n_mt) {
-                            mbar_wait(a_full + st, ph);
-                            fence_proxy_async_smem();  // the gather warps' cp.async writes (generic proxy) -> UMMA reads
-                            tc_fence_after_sync();
-                            const uint64_t a_desc = desc_hi | (uint64_t)((smem_u32(sA + (size_t)st * kTcAStage) & 0x3FFFFu) >> 4);
-                            const uint32_t d = tmem_base + (uint32_t)(mt * NT);
-                            const uint32_t first = (k > 0 || ch > 0) ? 1u : 0u;
-                            if (elect_one()) {
-                                for (int j = 0; j < nk; ++j)  // + 32 bytes of K per MMA = + 2 in the address field
-                                    umma_tf32(d, a_desc + 2 * j, b_desc + 2 * j, idesc, j > 0 ? 1u : first);
-                                umma_commit(a_empty + st);
-                            }
-                            __syncwarp();
-                        }
-                        if (++st == SA) { st = 0; ph ^= 1; }
-                    }
-                    if (elect_one()) umma_commit(b_empty + stb);
-                    __syncwarp();
-                    if (++stb == SB) { stb = 0; phb ^= 1; }
+        // ~130 cycles of R2UR traffic per MMA).
+        const int mt = warp - 9;
+        const uint32_t idesc = umma_idesc_tf32(NT);
+        const uint64_t desc_hi = umma_desc_sw128(0);  // everything but the start address
+        const uint32_t d = tmem_base + (uint32_t)(mt * NT);
+        int st = mt, ph = 0, stb = 0, phb = 0, tstep = 0;
+        for (int k = 0; k < K; ++k) {
+            for (int ch = 0; ch < nchunk; ++ch) {
+                mbar_wait(b_full + stb, phb);
+                const int nk = min(kTcChunk, c_in - ch * kTcChunk) / 8;  // MMAs (K = 8 each) in this chunk
+                const uint64_t b_desc = desc_hi | (uint64_t)((smem_u32(sB + (size_t)stb * NT * 128) & 0x3FFFFu) >> 4);
+                TC_STAMP(mt == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 4, tstep);
+                mbar_wait(a_full + st, ph);
+                TC_STAMP(mt == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 5, tstep);
+                fence_proxy_async_smem();  // the gather warps' cp.async writes (generic proxy) -> UMMA reads
+                tc_fence_after_sync();
+                const uint64_t a_desc = desc_hi | (uint64_t)((smem_u32(sA + (size_t)st * kTcAStage) & 0x3FFFFu) >> 4);
+                const uint32_t first = (k > 0 || ch > 0) ? 1u : 0u;
+                if (elect_one()) {
+                    for (int j = 0; j < nk; ++j)  // + 32 bytes of K per MMA = + 2 in the address field
+                        umma_tf32(d, a_desc + 2 * j, b_desc + 2 * j, idesc, j > 0 ? 1u : first);
+                    umma_commit(a_empty + st);
+                    umma_commit(b_empty + stb);  // n_mt arrivals (one per issuer) release the weight stage
                 }
+                __syncwarp();
+                TC_STAMP(mt == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 6, tstep);
+                ++tstep;
+                st += TPC;
+                if (st >= SA) { st -= SA; ph ^= 1; }
+                if (++stb == SB) { stb = 0; phb ^= 1; }
             }
-            if (elect_one()) umma_commit(d_full);
-            __syncwarp();
         }
+        if (elect_one()) umma_commit(d_full);  // n_mt arrivals complete it
+        __syncwarp();
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -323,14 +341,24 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
     // two CTAs per SM when that helps: not when the whole grid fits one CTA per SM anyway (then the one CTA gets all stages)
     bool two = want_ctas >= 2 && tc_tmem_cols(nt, tpc) <= 256 && (nt <= 64 || tpc == 1) &&
                ceil_div(gt.n_out, 128 * tpc) > kNumSMs;
+    // three CTAs per SM for the narrow, large levels (C_out <= 32): the gather warps are issue-latency bound, so more
+    // resident warps matter more than ring depth (a 4-stage ring measured the same as a 6-stage one at two CTAs per SM)
+    static const int want_three = [] { const char *e = getenv("MOPA_TC_THREE"); return e ? atoi(e) : 0; }();
+    const bool three = want_three && two && tpc == 2 && nt <= 32 && ceil_div(gt.n_out, kTcTM) > 2 * kNumSMs;
     int sa = 0;
     size_t cap = 0;
-    for (;;) {
-        cap = two ? (size_t)113 * 1024 : (size_t)226 * 1024;
-        sa = kTcMaxSA;
-        while (sa > 2 && (size_t)tc_smem_layout(nt, sa, sb).total + 1024 > cap) sa -= tpc;
-        if (!two || sa >= 4) break;
-        two = false;  // too few stages at two CTAs per SM: take the whole SM
+    if (three) {
+        sb = 2;
+        sa = 4;
+        cap = (size_t)75 * 1024;
+    } else {
+        for (;;) {
+            cap = two ? (size_t)113 * 1024 : (size_t)226 * 1024;
+            sa = kTcMaxSA;
+            while (sa > 2 && (size_t)tc_smem_layout(nt, sa, sb).total + 1024 > cap) sa -= tpc;
+            if (!two || sa >= 4) break;
+            two = false;  // too few stages at two CTAs per SM: take the whole SM
+        }
     }
     MOPA_CHECK((size_t)tc_smem_layout(nt, sa, sb).total + 1024 <= cap && sa >= 2, "conv_tc: shared memory layout does not fit");
     const size_t smem = (size_t)tc_smem_layout(nt, sa, sb).total + 1024;
@@ -346,3 +374,11 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
 }
 
 }  // namespace mopa
+
+#ifdef MOPA_TC_TRACE
+extern "C" int mopa_scn_debug_tc_trace(long long *host) {  // copies the timeline of the last launch out, then clears it
+    if (cudaMemcpyFromSymbol(host, mopa::g_tc_trace, sizeof(long long) * 8 * 512) != cudaSuccess) return 1;
+    static long long zeros[8 * 512];
+    return cudaMemcpyToSymbol(mopa::g_tc_trace, zeros, sizeof(zeros)) != cudaSuccess;
+}
+#endif

@@ -156,6 +156,14 @@ __device__ __forceinline__ void cp_async16_pred_s(uint32_t dst, const void *gmem
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(dst),
         "l"(gmem_src), "r"(src_bytes), "r"((int)pred));
 }
+// guarded copy with the ignore-src operand: @guard { dst[0..16) = zero ? 0 : src[0..16) }. One LDGSTS(.ZFILL) and two
+// predicate moves; the src-size register form makes ptxas emit address arithmetic around every copy.
+__device__ __forceinline__ void cp_async16_zfill_pred_s(uint32_t dst, const void *gmem_src, uint32_t guard, uint32_t zero) {
+    asm volatile(
+        "{\n\t.reg .pred pg, pz;\n\tsetp.ne.b32 pg, %2, 0;\n\tsetp.ne.b32 pz, %3, 0;\n\t"
+        "@pg cp.async.cg.shared.global [%0], [%1], 16, pz;\n\t}" ::"r"(dst),
+        "l"(gmem_src), "r"(guard), "r"(zero));
+}
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc_s(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }

@@ -1,6 +1,5 @@
-"""Timeline of one mid-grid CTA of a k_conv_tc launch (MOPA_TC_DBG=32): python scratch/tc_trace.py CIN COUT [scans]"""
+"""Timeline of one mid-grid CTA of a k_conv_tc launch. Needs a trace build: MOPA_BUILD_DEFS=MOPA_TC_TRACE python -m mopa_b200._build --force ; python scratch/tc_trace.py CIN COUT [CIN COUT ...]"""
 import ctypes, os, sys
-os.environ["MOPA_TC_DBG"] = str(32 | int(os.environ.get("EXTRA_DBG", "0")))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import mopa_b200.scn as scn
