@@ -174,14 +174,23 @@ def op_bytes_flops(rec):
 
 def roofline_pass(net, batches_dev, steps, peaks):
     """Per-launch device times from the library's own event log (CUDA events recorded on the launching stream around
-    each op's kernels, include/mopa_scn.h mopa_scn_Profile_*). Dominant kernel: k_gather_mma, the gather -> MMA ->
-    accumulate kernel every submanifold / strided convolution runs in forward and in the input-gradient pass."""
+    each op's kernels, include/mopa_scn.h mopa_scn_Profile_*). Dominant kernel: k_conv_tc, the tcgen05 gather -> MMA ->
+    TMEM-accumulate kernel every submanifold / strided convolution runs in forward and in the input-gradient pass.
+    During this pass the d_weight kernels stay on the main stream (MOPA_SCN_NO_DW_OVERLAP=1): in the timed steps they run
+    concurrently with the d_input kernels on a second stream, which would inflate per-kernel event times."""
     from mopa_b200 import _lib
+    prev = os.environ.get("MOPA_SCN_NO_DW_OVERLAP")
+    os.environ["MOPA_SCN_NO_DW_OVERLAP"] = "1"
     _lib.profile_enable(True)
     for i in range(steps):
         c, f = batches_dev[i % len(batches_dev)]
         out = net([c, f])
         out.sum().backward()
+    torch.cuda.synchronize()
+    if prev is None:
+        del os.environ["MOPA_SCN_NO_DW_OVERLAP"]
+    else:
+        os.environ["MOPA_SCN_NO_DW_OVERLAP"] = prev
     recs = _lib.profile_read()
     _lib.profile_enable(False)
     names = {1: "conv_forward", 2: "conv_d_input", 3: "conv_d_weight", 4: "bn_forward", 5: "bn_backward"}
@@ -199,8 +208,13 @@ def roofline_pass(net, batches_dev, steps, peaks):
     n = sum(cls[k][2] for k in ("conv_forward", "conv_d_input") if k in cls)
     fl = sum(cls[k][3] for k in ("conv_forward", "conv_d_input") if k in cls)
     ach = b / t / 1e9 if t > 0 else 0.0
-    return {"bound": "hbm", "kernel": "k_gather_mma (gather -> TF32 MMA -> accumulate; conv forward + d_input, %d launches/step)" % (n // max(steps, 1)),
-            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    traffic = None  # dram bytes per launch of the same launches, from one `ncu --set full` capture (profiles/README.md)
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_tc_traffic.json")))["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return {"bound": "hbm", "kernel": "k_conv_tc (tcgen05: cp.async gather -> TF32 UMMA -> TMEM accumulate; conv forward + d_input, %d launches/step)" % (n // max(steps, 1)),
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
             "launches_timed": n, "avg_launch_us": 1e6 * t / max(n, 1), "algorithmic_bytes_per_launch": b / max(n, 1),
             "tflops_useful": fl / t / 1e12 if t > 0 else 0.0,

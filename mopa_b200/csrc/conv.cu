@@ -750,6 +750,11 @@ int conv_dweight(const Gather &gt, const float *in, int64_t ld_in, const float *
     return 0;
 }
 
+bool conv_packs_tc(int c_in, int c_out, int precision) {
+    return precision != MOPA_SCN_PREC_FP32 && c_in % 16 == 0 && c_out % 16 == 0 && conv_uses_packed(c_in, c_out) &&
+           conv_tc_enabled() && conv_tc_supported(c_in, c_out);
+}
+
 int pack_weights(const float *weight, int volume, int n_in, int n_out, int transpose, int flip, int precision,
                  float *packed, cudaStream_t s) {
     const int c_in = transpose ? n_out : n_in, c_out = transpose ? n_in : n_out;

@@ -163,6 +163,11 @@ __global__ void __launch_bounds__(kDwTcThreads)
         const uint32_t row_a = (uint32_t)(rt >> 2) * (uint32_t)n_ma * 512 + (uint32_t)(rt & 3) * 128;
         const uint32_t row_b = (uint32_t)(rt >> 2) * (uint32_t)n_na * 512 + (uint32_t)(rt & 3) * 128;
         const uint32_t sw = (uint32_t)(rt & 3);
+        const uint32_t off0 = ((((uint32_t)sub4 >> 1) ^ sw) << 5) + (((uint32_t)sub4 & 1) << 4);        // piece sub4
+        const uint32_t off1 = (((((uint32_t)sub4 >> 1) + 2) ^ sw) << 5) + (((uint32_t)sub4 & 1) << 4);  // piece sub4 + 4
+        const char *src_m_c = reinterpret_cast<const char *>(src_m) + 16 * sub4;
+        const char *src_n_c = reinterpret_cast<const char *>(src_n) + 16 * sub4;
+        const uint32_t ldm_b = (uint32_t)ld_m * 4, ldn_b = (uint32_t)ld_n * 4;
         const uint32_t lt_mask = (1u << lane) - 1;
         int st = 0;
         uint32_t ph = 1;
@@ -170,22 +175,30 @@ __global__ void __launch_bounds__(kDwTcThreads)
 
         auto emit = [&](int count, uint32_t last) {
             mbar_wait_s(empty_a + 8 * st, ph);
-            const bool ok = rt < count;
-            int m_row = 0, n_row = 0;
-            if (ok) {
+            const uint32_t pad = rt < count ? 0u : 1u;  // rules beyond the end of the item: zero rows (ignore-src)
+            uint32_t m_row = 0, n_row = 0;
+            if (!pad) {
                 const uint32_t e = list_a + (uint32_t)((head + rt) & (kDwTcList - 1)) * 8;
-                m_row = (int)lds_u32(e);
-                n_row = (int)lds_u32(e + 4);
+                m_row = lds_u32(e);
+                n_row = lds_u32(e + 4);
             }
-            const int bytes = ok ? 16 : 0;  // 0: zero fill (rules beyond the end of the item)
-            const float *gm = src_m + (int64_t)m_row * ld_m, *gn = src_n + (int64_t)n_row * ld_n;
-            const uint32_t ta = a0 + (uint32_t)st * stage_a + row_a, tb = b0 + (uint32_t)st * stage_b + row_b;
-            for (int p = sub4; p < pm; p += 4)
-                cp_async16_s(ta + (uint32_t)(p >> 3) * 512 + (((((uint32_t)p & 7) >> 1) ^ sw) << 5) + (((uint32_t)p & 1) << 4),
-                             gm + 4 * p, bytes);
-            for (int p = sub4; p < pn; p += 4)
-                cp_async16_s(tb + (uint32_t)(p >> 3) * 512 + (((((uint32_t)p & 7) >> 1) ^ sw) << 5) + (((uint32_t)p & 1) << 4),
-                             gn + 4 * p, bytes);
+            // 32-bit row offsets (a feature matrix is far below 4 GB); this thread copies pieces sub4 and sub4 + 4 of every
+            // 32-channel atom: their swizzled offsets (off0, off1) do not depend on the atom
+            const char *gm = src_m_c + (uint64_t)m_row * (uint64_t)ldm_b;
+            const char *gn = src_n_c + (uint64_t)n_row * (uint64_t)ldn_b;
+            uint32_t ta = a0 + (uint32_t)st * stage_a + row_a, tb = b0 + (uint32_t)st * stage_b + row_b;
+            for (int p8 = 0; p8 < pm; p8 += 8) {
+                cp_async16_zfill_s(ta + off0, gm, pad);
+                if (p8 + 4 < pm) cp_async16_zfill_s(ta + off1, gm + 64, pad);
+                ta += 512;
+                gm += 128;
+            }
+            for (int p8 = 0; p8 < pn; p8 += 8) {
+                cp_async16_zfill_s(tb + off0, gn, pad);
+                if (p8 + 4 < pn) cp_async16_zfill_s(tb + off1, gn + 64, pad);
+                tb += 512;
+                gn += 128;
+            }
             if (tid == 0) {
                 sts_u32(info_a + 4 * st, last);
                 mbar_arrive_s(full_a + 8 * st);  // release: publishes the flag

@@ -49,11 +49,8 @@ __host__ __device__ inline int tc_tmem_cols(int nt, int tpc = 2) {  // power of 
 
 // packed[k][chunk][NT rows x 128 bytes, SWIZZLE_128B]: B operand (N x K, K-major) of one pipeline step.
 // element (n, c) of a chunk = W'[ci = 32 chunk + c][co = n], rounded to TF32 (zero for ci >= c_in).
-__global__ void __launch_bounds__(256) k_pack_weights_tc(const float *__restrict__ w, int volume, int n_in0, int n_out0,
-                                                         int transpose, int flip, float *__restrict__ packed,
-                                                         int64_t total) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
+__device__ __forceinline__ void tc_pack_element(const float *__restrict__ w, int volume, int n_in0, int n_out0, int transpose,
+                                                int flip, float *__restrict__ packed, int64_t idx) {
     const int c_in = transpose ? n_out0 : n_in0, nt = transpose ? n_in0 : n_out0;
     const int nchunk = (c_in + kTcChunk - 1) / kTcChunk;
     const int64_t per_chunk = (int64_t)nt * kTcChunk, per_k = per_chunk * nchunk;
@@ -69,6 +66,18 @@ __global__ void __launch_bounds__(256) k_pack_weights_tc(const float *__restrict
     float v = 0.f;
     if (ci < c_in) v = transpose ? w[((int64_t)ks * n_in0 + co) * n_out0 + ci] : w[((int64_t)ks * n_in0 + ci) * n_out0 + co];
     packed[idx] = __uint_as_float(to_tf32(v));
+}
+__global__ void __launch_bounds__(256) k_pack_weights_tc(const float *__restrict__ w, int volume, int n_in0, int n_out0,
+                                                         int transpose, int flip, float *__restrict__ packed,
+                                                         int64_t total) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < total) tc_pack_element(w, volume, n_in0, n_out0, transpose, flip, packed, idx);
+}
+// every convolution of a pass in one launch (grid.y = job): the whole-network executor packs all weights up front
+__global__ void __launch_bounds__(256) k_pack_weights_tc_batch(const __grid_constant__ TcPackJobs jobs) {
+    const TcPackJob &j = jobs.job[blockIdx.y];
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < j.total; idx += (int64_t)gridDim.x * blockDim.x)
+        tc_pack_element(j.w, j.volume, j.n_in, j.n_out, j.transpose, j.flip, j.packed, idx);
 }
 
 #ifdef MOPA_TC_TRACE
@@ -321,6 +330,24 @@ int pack_weights_tc(const float *weight, int volume, int n_in, int n_out, int tr
     const int64_t total = tc_packed_floats(volume, c_in, c_out);
     k_pack_weights_tc<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(weight, volume, n_in, n_out, transpose, flip, packed,
                                                                     total);
+    MOPA_LAUNCHED();
+    return 0;
+}
+
+int pack_weights_tc_batch(TcPackJobs &jobs, int n_jobs, cudaStream_t s) {
+    if (n_jobs == 0) return 0;
+    MOPA_CHECK(n_jobs <= kTcMaxPackJobs, "packWeights: too many jobs in one batch");
+    int64_t most = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        TcPackJob &j = jobs.job[i];
+        const int c_in = j.transpose ? j.n_out : j.n_in, c_out = j.transpose ? j.n_in : j.n_out;
+        MOPA_CHECK(conv_tc_supported(c_in, c_out), "packWeights: shape is not on the tcgen05 path");
+        j.total = tc_packed_floats(j.volume, c_in, c_out);
+        if (j.total > most) most = j.total;
+    }
+    int64_t bx = ceil_div(most, 256 * 4);  // ~4 elements per thread for the largest job
+    if (bx < 1) bx = 1;
+    k_pack_weights_tc_batch<<<dim3((unsigned)bx, (unsigned)n_jobs), 256, 0, s>>>(jobs);
     MOPA_LAUNCHED();
     return 0;
 }

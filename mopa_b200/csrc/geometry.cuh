@@ -77,6 +77,19 @@ bool conv_tc_supported(int c_in, int c_out);
 int64_t tc_packed_floats(int volume, int c_in, int c_out);
 int pack_weights_tc(const float *weight, int volume, int n_in, int n_out, int transpose, int flip, float *packed,
                     cudaStream_t s);
+// all weight packs of one pass in one launch (program.cu)
+constexpr int kTcMaxPackJobs = 40;
+struct TcPackJob {
+    const float *w;
+    float *packed;
+    int64_t total;  // filled by pack_weights_tc_batch
+    int volume, n_in, n_out, transpose, flip;
+};
+struct TcPackJobs {
+    TcPackJob job[kTcMaxPackJobs];
+};
+int pack_weights_tc_batch(TcPackJobs &jobs, int n_jobs, cudaStream_t s);
+bool conv_packs_tc(int c_in, int c_out, int precision);  // this shape's weights go through pack_weights_tc
 int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *packed,
                   int c_in, int c_out, cudaStream_t s);
 // tcgen05 d_weight (conv_dw_tc.cu): TF32 mode, channel counts that are multiples of 16

@@ -33,6 +33,7 @@ struct Layout {  // resolved per forward from the level sizes
     std::vector<size_t> buf_off;   // byte offset of root buffers in the activation / gradient arena
     std::vector<int64_t> buf_ld;   // row stride (floats) of every buffer
     std::vector<size_t> bn_off;    // per op: byte offset of (save_mean, save_invstd) in the activation arena
+    std::vector<size_t> pk_off;    // per conv op: byte offset of its packed weights in the scratch block
     size_t act_bytes = 0, grad_bytes = 0, packed_bytes = 0, dw_bytes = 0;
 };
 
@@ -112,7 +113,8 @@ static int make_layout(const mopa_scn_program *p, const mopa_scn_metadata *m, in
     }
     L.grad_bytes = off + 256;
     L.bn_off.assign(p->ops.size(), 0);
-    L.packed_bytes = 256;
+    L.pk_off.assign(p->ops.size(), 0);
+    L.packed_bytes = 0;
     L.dw_bytes = 256;
     for (size_t i = 0; i < p->ops.size(); ++i) {
         const POp &o = p->ops[i];
@@ -121,15 +123,43 @@ static int make_layout(const mopa_scn_program *p, const mopa_scn_metadata *m, in
             off += align256((size_t)2 * o.n_in * 4);
         } else {
             const int volume = o.type == OP_SUBM ? 27 : 8;
-            const size_t pk = (size_t)mopa_scn_packedWeightFloats(volume, o.n_in, o.n_out, precision) * 4;
-            if (pk > L.packed_bytes) L.packed_bytes = align256(pk);
+            L.pk_off[i] = L.packed_bytes;  // every op keeps its own slot: all packs of a pass are one launch
+            L.packed_bytes += align256((size_t)mopa_scn_packedWeightFloats(volume, o.n_in, o.n_out, precision) * 4);
             const int64_t rows = m->levels[o.level_out].V;  // d_weight chunks run over the op's OUTPUT rows
             const size_t dw = dw_workspace_bytes(volume, o.n_in, o.n_out, rows);
             if (dw > L.dw_bytes) L.dw_bytes = align256(dw);
         }
     }
+    L.packed_bytes += 256;
     L.act_bytes = off + 256;
     return 0;
+}
+
+// packs the weights of every convolution of a pass: the tcgen05 layouts in one launch, the others one by one
+static int pack_all(const mopa_scn_program *p, const Layout &L, const void *const *params, int precision, bool backward,
+                    const std::vector<char> *wanted, void *scratch, cudaStream_t s) {
+    TcPackJobs jobs;
+    int n = 0;
+    for (size_t i = 0; i < p->ops.size(); ++i) {
+        const POp &o = p->ops[i];
+        if (o.type == OP_BN || (wanted && !(*wanted)[i])) continue;
+        const int volume = o.type == OP_SUBM ? 27 : 8;
+        const int c_in = backward ? o.n_out : o.n_in, c_out = backward ? o.n_in : o.n_out;
+        if (!conv_uses_packed(c_in, c_out)) continue;
+        float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(scratch) + L.pk_off[i]);
+        const float *w = (const float *)params[o.param];
+        const int flip = backward && o.type == OP_SUBM ? 1 : 0;
+        if (conv_packs_tc(c_in, c_out, precision)) {
+            if (n == kTcMaxPackJobs) {
+                MOPA_TRY(pack_weights_tc_batch(jobs, n, s));
+                n = 0;
+            }
+            jobs.job[n++] = TcPackJob{w, dst, 0, volume, o.n_in, o.n_out, backward ? 1 : 0, flip};
+        } else {
+            MOPA_TRY(pack_weights(w, volume, o.n_in, o.n_out, backward ? 1 : 0, flip, precision, dst, s));
+        }
+    }
+    return pack_weights_tc_batch(jobs, n, s);
 }
 
 struct BufView {
@@ -238,7 +268,7 @@ int mopa_scn_Program_forward(mopa_scn_program *p, mopa_scn_metadata *m, const fl
     m->last_stream = s;
     Layout L;
     MOPA_TRY(make_layout(p, m, precision, L));
-    float *packed = reinterpret_cast<float *>(scratch);
+    MOPA_TRY(pack_all(p, L, params, precision, false, nullptr, scratch, s));
     BufView b0 = view(L, act_arena, p->in_buf);
     MOPA_TRY(mopa_scn_InputLayer_updateOutput(m, feats, ld_feats, p->in_planes, b0.ptr, b0.ld, s));
     for (size_t i = 0; i < p->ops.size(); ++i) {
@@ -254,11 +284,9 @@ int mopa_scn_Program_forward(mopa_scn_program *p, mopa_scn_metadata *m, const fl
         }
         const int volume = o.type == OP_SUBM ? 27 : 8;
         const float *w = (const float *)params[o.param];
-        const float *pk = nullptr;
-        if (conv_uses_packed(o.n_in, o.n_out)) {
-            MOPA_TRY(pack_weights(w, volume, o.n_in, o.n_out, 0, 0, precision, packed, s));
-            pk = packed;
-        }
+        const float *pk = conv_uses_packed(o.n_in, o.n_out)
+                              ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(scratch) + L.pk_off[i])
+                              : nullptr;
         MOPA_TRY(conv_apply(op_gather(o, m, false), in.ptr, in.ld, ob.ptr, ob.ld, w, pk, o.n_in, o.n_out, 0, 0, precision, s));
     }
     BufView last = view(L, act_arena, p->out_buf);
@@ -276,8 +304,13 @@ int mopa_scn_Program_backward(mopa_scn_program *p, mopa_scn_metadata *m, const v
     m->last_stream = s;
     Layout L;
     MOPA_TRY(make_layout(p, m, precision, L));
-    float *packed = reinterpret_cast<float *>(scratch);
     void *dw_ws = reinterpret_cast<char *>(scratch) + L.packed_bytes;
+    {  // transposed (and for 3x3x3, offset-flipped) weights of every op that produces an input gradient, one launch
+        std::vector<char> wanted(p->ops.size(), 0);
+        for (size_t i = 0; i < p->ops.size(); ++i)
+            wanted[i] = p->ops[i].type != OP_BN && (p->ops[i].in != p->in_buf || d_feats != nullptr);
+        MOPA_TRY(pack_all(p, L, params, precision, true, &wanted, scratch, s));
+    }
     void *act = const_cast<void *>(act_arena);
     const size_t nb = p->bufs.size();
     std::vector<char> written(nb, 0);
@@ -333,11 +366,9 @@ int mopa_scn_Program_backward(mopa_scn_program *p, mopa_scn_metadata *m, const v
                                       o.n_in, o.n_out, precision, dw_ws, L.dw_bytes, s2));
             }
             if (need_din) {
-                const float *pk = nullptr;
-                if (conv_uses_packed(o.n_out, o.n_in)) {
-                    MOPA_TRY(pack_weights(w, volume, o.n_in, o.n_out, 1, o.type == OP_SUBM ? 1 : 0, precision, packed, s));
-                    pk = packed;
-                }
+                const float *pk = conv_uses_packed(o.n_out, o.n_in)
+                                      ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(scratch) + L.pk_off[i])
+                                      : nullptr;
                 Gather g = op_gather(o, m, true);
                 g.accumulate = accumulate;
                 MOPA_TRY(conv_apply(g, dy.ptr, dy.ld, dx.ptr, dx.ld, w, pk, o.n_in, o.n_out, 1, o.type == OP_SUBM ? 1 : 0,

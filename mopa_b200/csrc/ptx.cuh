@@ -164,6 +164,11 @@ __device__ __forceinline__ void cp_async16_zfill_pred_s(uint32_t dst, const void
         "@pg cp.async.cg.shared.global [%0], [%1], 16, pz;\n\t}" ::"r"(dst),
         "l"(gmem_src), "r"(guard), "r"(zero));
 }
+// unguarded copy with the ignore-src operand: dst[0..16) = zero ? 0 : src[0..16)
+__device__ __forceinline__ void cp_async16_zfill_s(uint32_t dst, const void *gmem_src, uint32_t zero) {
+    asm volatile("{\n\t.reg .pred pz;\n\tsetp.ne.b32 pz, %2, 0;\n\tcp.async.cg.shared.global [%0], [%1], 16, pz;\n\t}" ::"r"(dst),
+                 "l"(gmem_src), "r"(zero));
+}
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc_s(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }

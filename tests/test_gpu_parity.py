@@ -185,6 +185,81 @@ def test_strided_conv_and_deconv_forward_backward(scn, precision, a, b):
     assert rel_err(f.grad, fo.grad) < 2 * tol
 
 
+@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 32), (64, 32)])
+def test_large_level_two_tile_ctas_and_strided_against_oracle(scn, cin, cout):
+    """> 148 x 256 rows: the tcgen05 conv kernel runs two M tiles per CTA with one issuer warp per tile, two CTAs per SM,
+    several waves; d_weight items span many producer passes and wrap the stage ring (the small cases above never do)."""
+    scn.set_precision("tf32")
+    tol = TOL_LAYER["tf32"]
+    coords = random_cloud(90000, 46, cin + cout, n_batch=1, dup_frac=0.05)
+    feats = np.random.default_rng(5).normal(size=(coords.shape[0], cin)).astype(np.float32)
+    x, f = _input(scn, coords, feats, size=64)
+    assert x.features.shape[0] > 148 * 256
+    conv = scn.SubmanifoldConvolution(3, cin, cout, 3, False).cuda()
+    down = scn.Convolution(3, cout, cout + 16, 2, 2, False).cuda()
+    y = conv(x)
+    z = down(y)
+    geo = so.Geometry(coords, 64)
+    fo = torch.from_numpy(feats).double().requires_grad_(True)
+    w = conv.weight.detach().cpu().double().requires_grad_(True)
+    wd = down.weight.detach().cpu().double().requires_grad_(True)
+    ry = so.submanifold_conv(geo, 0, so.input_layer_forward(geo, fo), w)
+    rz = so.strided_conv(geo, 0, ry, wd)
+    assert rel_err(y.features, ry) < tol and rel_err(z.features, rz) < 2 * tol
+    g = torch.randn(rz.shape, dtype=torch.float64)
+    z.features.backward(g.float().cuda())
+    rz.backward(g)
+    assert rel_err(down.weight.grad, wd.grad) < 2 * tol
+    assert rel_err(conv.weight.grad, w.grad) < 2 * tol
+    assert rel_err(f.grad, fo.grad) < 2 * tol
+
+
+def test_tcgen05_dweight_matches_mma_sync_kernel(scn, monkeypatch):
+    """A/B inside the library: d_weight from the tcgen05 kernel (rule-compacted MN-major operands) against the mma.sync
+    kernel it replaced (MOPA_SCN_NO_DWTC=1), submanifold (centre offset split) and deconvolution (select gather)."""
+    scn.set_precision("tf32")
+    coords = random_cloud(60000, 40, 77, n_batch=2, dup_frac=0.05)
+    feats = torch.randn(coords.shape[0], 48, generator=torch.Generator().manual_seed(3))
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MOPA_SCN_NO_DWTC", mode)
+        torch.manual_seed(0)
+        x, _ = _input(scn, coords, feats, size=64)
+        conv = scn.SubmanifoldConvolution(3, 48, 80, 3, False).cuda()
+        down = scn.Convolution(3, 80, 96, 2, 2, False).cuda()
+        up = scn.Deconvolution(3, 96, 64, 2, 2, False).cuda()
+        out = up(down(conv(x))).features
+        out.backward(torch.ones_like(out) * 0.01 + out.detach() * 0.1)
+        res[mode] = [m.weight.grad.clone() for m in (conv, down, up)]
+    for a, b in zip(res["0"], res["1"]):
+        assert rel_err(a, b) < 2e-3  # both are TF32 products with fp32 accumulation; they differ in rounding mode and order
+
+
+@pytest.mark.parametrize("planes", [16, 32, 96])
+def test_fused_batchnorm_matches_two_kernel_path_bitwise_inputs(scn, planes, monkeypatch):
+    """The cooperative single-kernel BatchNorm (statistics, grid barrier, apply) against the two-kernel path
+    (MOPA_SCN_NO_BNFUSED=1) on a level large enough for the full co-resident grid, several calls in a row (the fused
+    kernel alternates between two accumulator sets and must leave them clean)."""
+    coords = random_cloud(150000, 60, planes, n_batch=2, dup_frac=0.0)
+    feats = (torch.randn(coords.shape[0], planes, generator=torch.Generator().manual_seed(4)) * 3 + 1.5)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MOPA_SCN_NO_BNFUSED", mode)
+        x, f = _input(scn, coords, feats, size=64)
+        bn = scn.BatchNormLeakyReLU(planes, leakiness=0.1).cuda()
+        outs = []
+        for it in range(3):
+            y = bn(x)
+            (y.features * (it + 1.0)).sum().backward()
+            outs.append(y.features.detach().clone())
+        res[mode] = (outs, bn.weight.grad.clone(), bn.bias.grad.clone(), f.grad.clone(), bn.running_mean.clone(),
+                     bn.running_var.clone())
+    for a, b in zip(res["0"][0], res["1"][0]):
+        assert rel_err(a, b) < 1e-6
+    for i in range(1, 6):
+        assert rel_err(res["0"][i], res["1"][i]) < 1e-5
+
+
 @pytest.mark.parametrize("train", [True, False])
 @pytest.mark.parametrize("planes,leak", [(16, 0.0), (112, 0.0), (224, 0.333), (5, 0.0)])
 def test_batchnorm_forward_backward(scn, train, planes, leak):

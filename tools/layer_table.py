@@ -41,6 +41,8 @@ def main():
     ap.add_argument("--precision", default="tf32")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "layers.json"))
     a = ap.parse_args()
+    # per-op event times: keep the d_weight kernels on the main stream (in normal runs they overlap the d_input kernels)
+    os.environ["MOPA_SCN_NO_DW_OVERLAP"] = "1"
     from mopa_b200 import _lib, synth
     from mopa_b200.unet_scn import UNetSCN
     import mopa_b200.scn as scn
