@@ -449,7 +449,7 @@ static int launch_bn_fused(const BnShapeArgs &A, cudaStream_t s) {
         MOPA_CUDA(cudaGetDevice(&dev));
         MOPA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         MOPA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 16 * 1024));
-        if (occ > 2) occ = 2;
+        if (occ > 2) occ = 2;  // (4 blocks per SM measured slower: the grid barrier and the 2C atomics per block grow)
         MOPA_CHECK(occ >= 1 && sms >= 1, "BatchNormalization: the fused kernel does not fit on this device");
         max_blocks = occ * sms;
     }

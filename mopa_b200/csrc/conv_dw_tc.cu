@@ -389,11 +389,20 @@ int conv_dweight_tc(const Gather &gt, const float *in, int64_t ld_in, const floa
     const int swap = hi <= 128 ? (n_out > n_in) : (n_out < n_in);
     const int c_m = swap ? n_out : n_in, c_n = swap ? n_in : n_out;
     const int n_ma = (c_m + 31) / 32, n_na = (c_n + 31) / 32;
+    // The producers are issue-latency bound (ncu: 'wait' + 'selected' > 50 % of their samples), so resident warps matter
+    // more than ring depth: as many CTAs per SM (up to 4) as still leave every CTA a ring of >= 3 stages.
     const size_t stage_bytes = (size_t)(n_ma + n_na) * 4096;
-    const size_t budget = stage_bytes <= 16 * 1024 ? (size_t)100 * 1024 : (size_t)200 * 1024;
-    int stages = (int)(budget / stage_bytes);
-    if (stages > kDwTcMaxStages) stages = kDwTcMaxStages;
-    if (stages < 2) stages = 2;
+    const size_t fixed = (size_t)dw_tc_smem(n_ma, n_na, 0).total + 2048;  // list, flags, barriers, alignment, per-CTA reserve
+    int stages = 2;
+    for (int ctas = 4; ctas >= 1; --ctas) {
+        const size_t per_cta = (size_t)227 * 1024 / ctas;
+        if (per_cta <= fixed) continue;
+        const int st = (int)((per_cta - fixed) / stage_bytes);
+        if (st >= (ctas == 1 ? 2 : 3)) {
+            stages = st > kDwTcMaxStages ? kDwTcMaxStages : st;
+            break;
+        }
+    }
     const size_t smem = (size_t)dw_tc_smem(n_ma, n_na, stages).total + 1024;
     static bool configured = false;
     if (!configured) {

@@ -180,13 +180,12 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         const int NP = LPR;                      // passes per step: 32 rows / (32 / LPR rows per pass)
         const int cl = lane & (LPR - 1);         // this lane's 16-byte piece
         const int rl = lane / LPR;               // row inside a pass
-        uint32_t bit[8], doff[8];
-        int rj[8];
+        uint32_t doff[8];
+        int rj[8];  // row of pass j (32 for the passes a narrow layout does not have: its bit shifts out)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int r = (j * (32 / LPR) + rl) & 31;
-            rj[j] = r;
-            bit[j] = j < NP ? 1u << r : 0u;
+            rj[j] = j < NP ? r : 32;
             doff[j] = (uint32_t)r * 128 + (uint32_t)((cl ^ (r & 7)) << 4);
         }
         const char *in_c = reinterpret_cast<const char *>(in) + 16 * cl;
@@ -196,7 +195,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
             const char *rp[8];  // source row of each pass (row 0 where there is no rule: never read, must be mapped)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int srow = __shfl_sync(0xffffffffu, nv, rj[j]);
+                const int srow = __shfl_sync(0xffffffffu, nv, rj[j] & 31);
                 rp[j] = in_c + (uint64_t)(uint32_t)max(srow, 0) * (uint64_t)ldb;
             }
             for (int ch = 0; ch < nchunk; ++ch) {
@@ -211,8 +210,10 @@ __global__ void __launch_bounds__(kTcThreads, 2)
                 const int cho = ch * (kTcChunk * 4);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const uint32_t is_new = a_new & bit[j];
-                    cp_async16_zfill_pred_s(tile_a + doff[j], rp[j] + cho, is_new | (a_old & bit[j]), is_new == 0u);
+                    // bit of this pass's row: clamped funnel shift, so that a shift count of 32 yields 0 (absent pass)
+                    const uint32_t is_new = __funnelshift_rc(a_new, 0u, rj[j]) & 1u;
+                    cp_async16_zfill_pred_s(tile_a + doff[j], rp[j] + cho, is_new | (__funnelshift_rc(a_old, 0u, rj[j]) & 1u),
+                                            is_new ^ 1u);
                 }
                 // every lane: "my copies of this step have landed" arrives on the stage's barrier asynchronously (128
                 // arrivals complete it); the warp never waits for data, so all stages of the ring can be in flight
