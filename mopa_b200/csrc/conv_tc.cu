@@ -92,22 +92,23 @@ __device__ long long g_tc_trace[8][512];
 struct TcSmem {  // byte offsets inside the dynamic shared memory block (base aligned to 1024)
     int a, b, mask, bars, total;
 };
-__host__ __device__ inline TcSmem tc_smem_layout(int nt, int sa, int sb) {
+__host__ __device__ inline TcSmem tc_smem_layout(int nt, int sa, int sb, int na = 1) {  // na: 32-channel atoms per stage
     TcSmem L;
     L.a = 0;
-    L.b = L.a + sa * kTcAStage;
-    L.mask = L.b + sb * nt * 128;
+    L.b = L.a + sa * na * kTcAStage;
+    L.mask = L.b + sb * na * nt * 128;
     L.bars = L.mask + 64;
     L.total = L.bars + 8 * (2 * kTcMaxSA + 2 * kTcMaxSB + 1) + 16;
     return L;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 2)
+template <int NA>
+__global__ void __launch_bounds__(kTcThreads, NA == 2 ? 1 : 2)  // the two-atom variant only runs one CTA per SM
     k_conv_tc(Gather gt, const float *__restrict__ in, int64_t ld_in, float *__restrict__ out, int64_t ld_out,
               const float *__restrict__ packed, int c_in, int NT, int SA, int SB, int TPC) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    const TcSmem L = tc_smem_layout(NT, SA, SB);
+    const TcSmem L = tc_smem_layout(NT, SA, SB, NA);
     unsigned char *sA = smem + L.a, *sB = smem + L.b;
     uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + L.bars), *a_empty = a_full + kTcMaxSA;
     uint64_t *b_full = a_empty + kTcMaxSA, *b_empty = b_full + kTcMaxSB;
@@ -116,7 +117,12 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = gt.volume;
-    const int nchunk = (c_in + kTcChunk - 1) / kTcChunk;
+    // NA = 32-channel atoms per pipeline step (1, or 2 on the small levels: their CTAs are alone on an SM and bound by
+    // the per-step latency, so half as many, twice as wide steps)
+    const int chw = kTcChunk * NA;                       // channels per step
+    const int nchunk = (c_in + chw - 1) / chw;           // steps per offset
+    const int nchunk32 = (c_in + kTcChunk - 1) / kTcChunk;  // packed weight chunks per offset
+    const uint32_t a_stage = (uint32_t)NA * kTcAStage, b_stage = (uint32_t)NA * NT * 128;
     // TPC = M tiles per CTA: 2 for the large levels; 1 for levels too small to fill the GPU with 256-row CTAs (twice
     // the CTAs, and the whole stage ring serves the one tile)
     const int64_t row0 = (int64_t)blockIdx.x * (128 * TPC);
@@ -131,7 +137,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     }
     if (warp == 9) tmem_alloc(tmem_ptr, tmem_cols);
     if (warp < 8) {  // all A stages start all-zero; nothing has been written by any warp yet
-        for (int i = tid; i < SA * kTcAStage / 16; i += 256) reinterpret_cast<float4 *>(sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < SA * NA * kTcAStage / 16; i += 256) reinterpret_cast<float4 *>(sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -199,21 +205,36 @@ __global__ void __launch_bounds__(kTcThreads, 2)
                 rp[j] = in_c + (uint64_t)(uint32_t)max(srow, 0) * (uint64_t)ldb;
             }
             for (int ch = 0; ch < nchunk; ++ch) {
-                const uint32_t pieces = (uint32_t)min(kTcChunk, c_in - ch * kTcChunk) / 4;  // 16-byte pieces per row
+                // 16-byte pieces per row in each 32-channel atom of this step (the last step of an offset may be short)
+                const int left = c_in - ch * chw;
+                const uint32_t pa0 = (uint32_t)min(kTcChunk, left) / 4, pa1 = NA == 2 ? (uint32_t)max(0, min(kTcChunk, left - kTcChunk)) / 4 : 0u;
+                const uint32_t pieces = pa0 | (pa1 << 8);
                 TC_STAMP(warp == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 0, tstep);
                 mbar_wait_s(empty0_a + 8 * st, ph);
                 TC_STAMP(warp == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 1, tstep);
                 const uint32_t m_old = __shfl_sync(0xffffffffu, oldm, st), p_old = __shfl_sync(0xffffffffu, oldp, st);
-                const uint32_t a_new = (uint32_t)cl < pieces ? m_new : 0u;  // rows this lane copies / may have to clear
-                const uint32_t a_old = (uint32_t)cl < p_old ? m_old : 0u;
-                const uint32_t tile_a = tile0_a + st * kTcAStage;
-                const int cho = ch * (kTcChunk * 4);
+                const uint32_t tile_a = tile0_a + st * a_stage;
+                const int cho = ch * (chw * 4);
+                {
+                    const uint32_t a_new = (uint32_t)cl < pa0 ? m_new : 0u;  // rows this lane copies / may have to clear
+                    const uint32_t a_old = (uint32_t)cl < (p_old & 0xffu) ? m_old : 0u;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    // bit of this pass's row: clamped funnel shift, so that a shift count of 32 yields 0 (absent pass)
-                    const uint32_t is_new = __funnelshift_rc(a_new, 0u, rj[j]) & 1u;
-                    cp_async16_zfill_pred_s(tile_a + doff[j], rp[j] + cho, is_new | (__funnelshift_rc(a_old, 0u, rj[j]) & 1u),
-                                            is_new ^ 1u);
+                    for (int j = 0; j < 8; ++j) {
+                        // bit of this pass's row: clamped funnel shift, so that a shift count of 32 yields 0 (absent pass)
+                        const uint32_t is_new = __funnelshift_rc(a_new, 0u, rj[j]) & 1u;
+                        cp_async16_zfill_pred_s(tile_a + doff[j], rp[j] + cho, is_new | (__funnelshift_rc(a_old, 0u, rj[j]) & 1u),
+                                                is_new ^ 1u);
+                    }
+                }
+                if (NA == 2) {  // second atom of the step: channels [32, 64) of the chunk, 16 KB further in the stage
+                    const uint32_t a_new = (uint32_t)cl < pa1 ? m_new : 0u;
+                    const uint32_t a_old = (uint32_t)cl < (p_old >> 8) ? m_old : 0u;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t is_new = __funnelshift_rc(a_new, 0u, rj[j]) & 1u;
+                        cp_async16_zfill_pred_s(tile_a + kTcAStage + doff[j], rp[j] + cho + 128,
+                                                is_new | (__funnelshift_rc(a_old, 0u, rj[j]) & 1u), is_new ^ 1u);
+                    }
                 }
                 // every lane: "my copies of this step have landed" arrives on the stage's barrier asynchronously (128
                 // arrivals complete it); the warp never waits for data, so all stages of the ring can be in flight
@@ -259,15 +280,17 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     } else if (warp == 8) {
         // ================================================================= weight producer (TMA bulk copies)
         if (lane == 0) {
-            const uint32_t bytes = (uint32_t)NT * 128;
-            const int n_steps = K * nchunk;
             int st = 0, ph = 1;
-            for (int sb = 0; sb < n_steps; ++sb) {
-                mbar_wait(b_empty + st, ph);
-                mbar_expect_tx(b_full + st, bytes);
-                tma_load_1d(sB + (size_t)st * bytes, packed + (int64_t)sb * NT * kTcChunk, bytes, b_full + st);
-                if (++st == SB) { st = 0; ph ^= 1; }
-            }
+            for (int k = 0; k < K; ++k)
+                for (int ch = 0; ch < nchunk; ++ch) {
+                    const int n32 = min(NA, nchunk32 - ch * NA);  // packed 32-channel chunks in this step (contiguous)
+                    const uint32_t bytes = (uint32_t)n32 * NT * 128;
+                    mbar_wait(b_empty + st, ph);
+                    mbar_expect_tx(b_full + st, bytes);
+                    tma_load_1d(sB + (size_t)st * b_stage, packed + ((int64_t)k * nchunk32 + ch * NA) * NT * kTcChunk, bytes,
+                                b_full + st);
+                    if (++st == SB) { st = 0; ph ^= 1; }
+                }
         }
     } else if (warp - 9 < n_mt) {
         // ================================================================= MMA issuers: warp 9 -> M tile 0, warp 10 -> M tile 1
@@ -284,18 +307,22 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         for (int k = 0; k < K; ++k) {
             for (int ch = 0; ch < nchunk; ++ch) {
                 mbar_wait(b_full + stb, phb);
-                const int nk = min(kTcChunk, c_in - ch * kTcChunk) / 8;  // MMAs (K = 8 each) in this chunk
-                const uint64_t b_desc = desc_hi | (uint64_t)((smem_u32(sB + (size_t)stb * NT * 128) & 0x3FFFFu) >> 4);
+                const int left = c_in - ch * chw;
+                const int nk0 = min(kTcChunk, left) / 8;                                   // MMAs (K = 8 each) from atom 0
+                const int nk1 = NA == 2 ? max(0, min(kTcChunk, left - kTcChunk)) / 8 : 0;  // ... and from atom 1
+                const uint64_t b_desc = desc_hi | (uint64_t)((smem_u32(sB + (size_t)stb * b_stage) & 0x3FFFFu) >> 4);
                 TC_STAMP(mt == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 4, tstep);
                 mbar_wait(a_full + st, ph);
                 TC_STAMP(mt == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 5, tstep);
                 fence_proxy_async_smem();  // the gather warps' cp.async writes (generic proxy) -> UMMA reads
                 tc_fence_after_sync();
-                const uint64_t a_desc = desc_hi | (uint64_t)((smem_u32(sA + (size_t)st * kTcAStage) & 0x3FFFFu) >> 4);
+                const uint64_t a_desc = desc_hi | (uint64_t)((smem_u32(sA + (size_t)st * a_stage) & 0x3FFFFu) >> 4);
                 const uint32_t first = (k > 0 || ch > 0) ? 1u : 0u;
                 if (elect_one()) {
-                    for (int j = 0; j < nk; ++j)  // + 32 bytes of K per MMA = + 2 in the address field
+                    for (int j = 0; j < nk0; ++j)  // + 32 bytes of K per MMA = + 2 in the address field
                         umma_tf32(d, a_desc + 2 * j, b_desc + 2 * j, idesc, j > 0 ? 1u : first);
+                    for (int j = 0; j < nk1; ++j)  // second atom: 16 KB further in A, NT x 128 bytes further in B
+                        umma_tf32(d, a_desc + (kTcAStage >> 4) + 2 * j, b_desc + (uint64_t)((NT * 128) >> 4) + 2 * j, idesc, 1u);
                     umma_commit(a_empty + st);
                     umma_commit(b_empty + stb);  // n_mt arrivals (one per issuer) release the weight stage
                 }
@@ -365,7 +392,10 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
     // streamed per CTA: halving the rows per CTA doubles that traffic, which costs more than it gains on mid-size levels)
     const int tpc = want_tpc ? want_tpc : (ceil_div(gt.n_out, kTcTM) > kNumSMs ? 2 : 1);
     int sb = want_sb < 2 ? 2 : (want_sb > kTcMaxSB ? kTcMaxSB : want_sb);
-    while (sb > 2 && (size_t)sb * nt * 128 > (size_t)(tpc == 2 ? 64 : 32) * 1024) --sb;
+    // two 32-channel atoms per step on the small levels (one CTA per SM, bound by the per-step latency)
+    static const int want_na = [] { const char *e = getenv("MOPA_TC_NA"); return e ? atoi(e) : 0; }();
+    const int na = want_na ? want_na : ((tpc == 1 && c_in >= 64 && ceil_div(gt.n_out, 128) <= kNumSMs) ? 2 : 1);
+    while (sb > 2 && (size_t)sb * na * nt * 128 > (size_t)(tpc == 2 ? 64 : 32 * na) * 1024) --sb;
     // two CTAs per SM when that helps: not when the whole grid fits one CTA per SM anyway (then the one CTA gets all stages)
     bool two = want_ctas >= 2 && tc_tmem_cols(nt, tpc) <= 256 && (nt <= 64 || tpc == 1) &&
                ceil_div(gt.n_out, 128 * tpc) > kNumSMs;
@@ -383,20 +413,24 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
         for (;;) {
             cap = two ? (size_t)113 * 1024 : (size_t)226 * 1024;
             sa = kTcMaxSA;
-            while (sa > 2 && (size_t)tc_smem_layout(nt, sa, sb).total + 1024 > cap) sa -= tpc;
+            while (sa > 2 && (size_t)tc_smem_layout(nt, sa, sb, na).total + 1024 > cap) sa -= tpc;
             if (!two || sa >= 4) break;
             two = false;  // too few stages at two CTAs per SM: take the whole SM
         }
     }
-    MOPA_CHECK((size_t)tc_smem_layout(nt, sa, sb).total + 1024 <= cap && sa >= 2, "conv_tc: shared memory layout does not fit");
-    const size_t smem = (size_t)tc_smem_layout(nt, sa, sb).total + 1024;
+    MOPA_CHECK((size_t)tc_smem_layout(nt, sa, sb, na).total + 1024 <= cap && sa >= 2, "conv_tc: shared memory layout does not fit");
+    const size_t smem = (size_t)tc_smem_layout(nt, sa, sb, na).total + 1024;
     static bool configured = false;
     if (!configured) {
-        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
     dim3 grid((unsigned)ceil_div(gt.n_out, 128 * tpc));
-    k_conv_tc<<<grid, kTcThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc);
+    if (na == 2)
+        k_conv_tc<2><<<grid, kTcThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc);
+    else
+        k_conv_tc<1><<<grid, kTcThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc);
     MOPA_LAUNCHED();
     return 0;
 }
