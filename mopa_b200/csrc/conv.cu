@@ -263,36 +263,91 @@ __global__ void __launch_bounds__(kConvThreads, conv_min_blocks(MT, NP, SPLIT)) 
 }
 
 // ------------------------------------------------------------------------------------------------ small-c_in conv
-// The 1 -> 16 input layer (scn_unet.py:27): one thread per output row and block of 16 output channels, weights in
-// shared memory, table reads coalesced across the warp. out[o][co] = sum_k sum_ci in[T[k][o]][ci] * W[k][ci][co].
+// The 1 -> 16 input layer (scn_unet.py:27): four threads per output row, four output channels each (a warp writes 8
+// rows = 512 contiguous bytes), weights in shared memory, all table reads of a 9-offset group in flight before the
+// first feature read. out[o][co] = sum_k sum_ci in[T[k][o]][ci] * W[k][ci][co]. HBM-bound: table 4 K V + out 4 V Cout.
 __global__ void __launch_bounds__(256) k_conv_smallcin(Gather gt, const float *__restrict__ in, int64_t ld_in,
                                                        float *__restrict__ out, int64_t ld_out,
                                                        const float *__restrict__ w, int c_in, int c_out) {
-    extern __shared__ float sw[];  // [K][c_in][c_out]
+    extern __shared__ __align__(16) float sw[];  // [K][c_in][c_out]
     for (int i = threadIdx.x; i < gt.volume * c_in * c_out; i += blockDim.x) sw[i] = w[i];
     __syncthreads();
-    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int cb = blockIdx.y * 16;
+    const int64_t o = (int64_t)blockIdx.x * 64 + (threadIdx.x >> 2);
+    const int cb = blockIdx.y * 16 + 4 * (threadIdx.x & 3);
     if (o >= gt.n_out) return;
-    float acc[16];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k0 = 0; k0 < gt.volume; k0 += 9) {
+        int idx[9];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-    for (int k = 0; k < gt.volume; ++k) {
-        const int i = gather_lookup(gt, k, o);
-        if (i < 0) continue;
+        for (int u = 0; u < 9; ++u) idx[u] = k0 + u < gt.volume ? gather_lookup(gt, k0 + u, o) : -1;
         for (int ci = 0; ci < c_in; ++ci) {
-            const float x = __ldg(in + (int64_t)i * ld_in + ci);
-            const float *wr = sw + (k * c_in + ci) * c_out + cb;
+            float x[9];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) acc[c] = fmaf(x, wr[c], acc[c]);
+            for (int u = 0; u < 9; ++u) x[u] = idx[u] >= 0 ? __ldg(in + (int64_t)idx[u] * ld_in + ci) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 9; ++u) {
+                if (k0 + u < gt.volume) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(sw + ((k0 + u) * c_in + ci) * c_out + cb);
+                    acc.x = fmaf(x[u], wv.x, acc.x); acc.y = fmaf(x[u], wv.y, acc.y);
+                    acc.z = fmaf(x[u], wv.z, acc.z); acc.w = fmaf(x[u], wv.w, acc.w);
+                }
+            }
         }
     }
-    float *dst = out + o * ld_out + cb;
+    float4 *dst = reinterpret_cast<float4 *>(out + o * ld_out + cb);
+    if (gt.accumulate) { const float4 e = *dst; acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w; }
+    *dst = acc;
+}
+
+// d_weight of the 1 -> 16 input layer: dW[k][0][co] = sum_o in[T[k][o]] * dout[o][co]. One pass over d_out and the table
+// (the generic kernel re-read d_out once per offset): four threads per row (4 channels each) keep all 27 x 4 partial sums
+// in registers; warp shuffles, then shared memory, reduce a block to one slice; k_dw_reduce sums the slices in order.
+__global__ void __launch_bounds__(256) k_dw_cin1(Gather gt, const float *__restrict__ in, int64_t ld_in,
+                                                 const float *__restrict__ dout, int64_t ld_dout,
+                                                 float *__restrict__ partial) {
+    __shared__ float red[8][27 * 16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = tid & 3;
+    float4 acc[27];
 #pragma unroll
-    for (int c = 0; c < 16; c += 4) {
-        float4 v = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-        if (gt.accumulate) { const float4 e = *reinterpret_cast<float4 *>(dst + c); v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
-        *reinterpret_cast<float4 *>(dst + c) = v;
+    for (int k = 0; k < 27; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t o = (int64_t)blockIdx.x * 64 + (tid >> 2); o < gt.n_out; o += (int64_t)gridDim.x * 64) {
+        const float4 d = *reinterpret_cast<const float4 *>(dout + o * ld_dout + 4 * q);
+#pragma unroll
+        for (int k0 = 0; k0 < 27; k0 += 9) {
+            int idx[9];
+            float x[9];
+#pragma unroll
+            for (int u = 0; u < 9; ++u) idx[u] = gather_lookup(gt, k0 + u, o);
+#pragma unroll
+            for (int u = 0; u < 9; ++u) x[u] = idx[u] >= 0 ? __ldg(in + (int64_t)idx[u] * ld_in) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 9; ++u) {
+                float4 &a = acc[k0 + u];
+                a.x = fmaf(x[u], d.x, a.x); a.y = fmaf(x[u], d.y, a.y); a.z = fmaf(x[u], d.z, a.z); a.w = fmaf(x[u], d.w, a.w);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        float v[4] = {acc[k].x, acc[k].y, acc[k].z, acc[k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[e] += __shfl_xor_sync(0xffffffffu, v[e], 4);
+            v[e] += __shfl_xor_sync(0xffffffffu, v[e], 8);
+            v[e] += __shfl_xor_sync(0xffffffffu, v[e], 16);
+        }
+        if (lane < 4) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) red[warp][k * 16 + 4 * q + e] = v[e];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 27 * 16; i += 256) {
+        float sum = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < 8; ++wi) sum += red[wi][i];
+        const int k = i >> 4, co = i & 15;
+        partial[((int64_t)k * gridDim.x + blockIdx.x) * 16 + co] = sum;  // k_dw_reduce layout: [k][slice][mat]
     }
 }
 
@@ -617,7 +672,7 @@ int conv_apply(const Gather &gt, const float *in, int64_t ld_in, float *out, int
                       ld_out % 4 == 0 && aligned16(packed);
     if (!fast && !transpose && !flip && c_in <= 8 && c_out % 16 == 0 && (size_t)gt.volume * c_in * c_out * 4 <= 40 * 1024 &&
         weight && aligned16(out) && ld_out % 4 == 0) {
-        dim3 grid((unsigned)ceil_div(gt.n_out, 256), c_out / 16);
+        dim3 grid((unsigned)ceil_div(gt.n_out, 64), c_out / 16);
         k_conv_smallcin<<<grid, 256, (size_t)gt.volume * c_in * c_out * 4, s>>>(gt, in, ld_in, out, ld_out, weight, c_in, c_out);
         MOPA_LAUNCHED();
         return 0;
@@ -680,6 +735,10 @@ size_t dw_workspace_bytes(int volume, int n_in, int n_out, int64_t n_rows) {
         const size_t t = dw_tc_workspace_bytes(volume, n_in, n_out, n_rows);
         if (t > b) b = t;
     }
+    if (n_in == 1 && n_out == 16 && volume == 27) {  // k_dw_cin1: one slice per block, at most one block per SM
+        const size_t t = (size_t)kNumSMs * 27 * 16 * 4;
+        if (t > b) b = t;
+    }
     return b + 256;
 }
 
@@ -737,6 +796,12 @@ int conv_dweight(const Gather &gt, const float *in, int64_t ld_in, const float *
             default: MOPA_FAIL("d_weight: channel counts too large");
         }
 #undef MOPA_DW
+    } else if (n_in == 1 && n_out == 16 && gt.volume == 27 && aligned16(dout) && ld_dout % 4 == 0 &&
+               (size_t)kNumSMs * 27 * 16 * 4 <= workspace_bytes) {
+        p.WK = 1;
+        p.per_k = (int)(ceil_div(gt.n_out, 64) < kNumSMs ? ceil_div(gt.n_out, 64) : kNumSMs);
+        k_dw_cin1<<<p.per_k, 256, 0, s>>>(gt, in, ld_in, dout, ld_dout, partial);
+        MOPA_LAUNCHED();
     } else {
         p.WK = 1;
         p.per_k = p.nchunks;
