@@ -261,7 +261,7 @@ def run_ours(a):
         loss = out.sum()
         loss.backward()
         bucket.all_reduce()
-        return float(loss)  # D2H read of the step's result
+        return float(loss.detach())  # D2H read of the step's result
 
     def barrier():
         if world > 1:

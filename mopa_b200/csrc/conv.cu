@@ -299,58 +299,6 @@ __global__ void __launch_bounds__(256) k_conv_smallcin(Gather gt, const float *_
     *dst = acc;
 }
 
-// d_weight of the 1 -> 16 input layer: dW[k][0][co] = sum_o in[T[k][o]] * dout[o][co]. One pass over d_out and the table
-// (the generic kernel re-read d_out once per offset): four threads per row (4 channels each) keep all 27 x 4 partial sums
-// in registers; warp shuffles, then shared memory, reduce a block to one slice; k_dw_reduce sums the slices in order.
-__global__ void __launch_bounds__(256) k_dw_cin1(Gather gt, const float *__restrict__ in, int64_t ld_in,
-                                                 const float *__restrict__ dout, int64_t ld_dout,
-                                                 float *__restrict__ partial) {
-    __shared__ float red[8][27 * 16];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = tid & 3;
-    float4 acc[27];
-#pragma unroll
-    for (int k = 0; k < 27; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t o = (int64_t)blockIdx.x * 64 + (tid >> 2); o < gt.n_out; o += (int64_t)gridDim.x * 64) {
-        const float4 d = *reinterpret_cast<const float4 *>(dout + o * ld_dout + 4 * q);
-#pragma unroll
-        for (int k0 = 0; k0 < 27; k0 += 9) {
-            int idx[9];
-            float x[9];
-#pragma unroll
-            for (int u = 0; u < 9; ++u) idx[u] = gather_lookup(gt, k0 + u, o);
-#pragma unroll
-            for (int u = 0; u < 9; ++u) x[u] = idx[u] >= 0 ? __ldg(in + (int64_t)idx[u] * ld_in) : 0.f;
-#pragma unroll
-            for (int u = 0; u < 9; ++u) {
-                float4 &a = acc[k0 + u];
-                a.x = fmaf(x[u], d.x, a.x); a.y = fmaf(x[u], d.y, a.y); a.z = fmaf(x[u], d.z, a.z); a.w = fmaf(x[u], d.w, a.w);
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 27; ++k) {
-        float v[4] = {acc[k].x, acc[k].y, acc[k].z, acc[k].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            v[e] += __shfl_xor_sync(0xffffffffu, v[e], 4);
-            v[e] += __shfl_xor_sync(0xffffffffu, v[e], 8);
-            v[e] += __shfl_xor_sync(0xffffffffu, v[e], 16);
-        }
-        if (lane < 4) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) red[warp][k * 16 + 4 * q + e] = v[e];
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < 27 * 16; i += 256) {
-        float sum = 0.f;
-#pragma unroll
-        for (int wi = 0; wi < 8; ++wi) sum += red[wi][i];
-        const int k = i >> 4, co = i & 15;
-        partial[((int64_t)k * gridDim.x + blockIdx.x) * 16 + co] = sum;  // k_dw_reduce layout: [k][slice][mat]
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ generic SIMT conv
 // Shapes the MMA path does not cover (channel counts that are not multiples of 16: the 1 -> 16 input layer).
 // out[o][co] = sum_k sum_ci in[T[k][o]][ci] * Wm[k][ci][co], Wm read from the unpacked (volume, n_in0, n_out0) weight.
@@ -735,10 +683,6 @@ size_t dw_workspace_bytes(int volume, int n_in, int n_out, int64_t n_rows) {
         const size_t t = dw_tc_workspace_bytes(volume, n_in, n_out, n_rows);
         if (t > b) b = t;
     }
-    if (n_in == 1 && n_out == 16 && volume == 27) {  // k_dw_cin1: one slice per block, at most one block per SM
-        const size_t t = (size_t)kNumSMs * 27 * 16 * 4;
-        if (t > b) b = t;
-    }
     return b + 256;
 }
 
@@ -796,12 +740,6 @@ int conv_dweight(const Gather &gt, const float *in, int64_t ld_in, const float *
             default: MOPA_FAIL("d_weight: channel counts too large");
         }
 #undef MOPA_DW
-    } else if (n_in == 1 && n_out == 16 && gt.volume == 27 && aligned16(dout) && ld_dout % 4 == 0 &&
-               (size_t)kNumSMs * 27 * 16 * 4 <= workspace_bytes) {
-        p.WK = 1;
-        p.per_k = (int)(ceil_div(gt.n_out, 64) < kNumSMs ? ceil_div(gt.n_out, 64) : kNumSMs);
-        k_dw_cin1<<<p.per_k, 256, 0, s>>>(gt, in, ld_in, dout, ld_dout, partial);
-        MOPA_LAUNCHED();
     } else {
         p.WK = 1;
         p.per_k = p.nchunks;
