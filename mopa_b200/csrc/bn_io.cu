@@ -410,6 +410,63 @@ __global__ void __launch_bounds__(256) k_bn_fused(const float *__restrict__ x, i
 template <int VEC, bool BWD>
 static int launch_bn_fused(const BnShapeArgs &A, cudaStream_t s);
 
+// ---- train-mode forward when the producing convolution already accumulated the column sums (conv_tc epilogue):
+// every block derives mean / invstd from the fp64 sums (sum x, sum x^2) and applies them; no statistics pass, no barrier.
+template <int VEC>
+__global__ void __launch_bounds__(256) k_bn_apply_sums(const float *__restrict__ x, int64_t ld_x, float *__restrict__ out,
+                                                       int64_t ld_out, int64_t n, int planes,
+                                                       const double *__restrict__ sums, const float *__restrict__ weight,
+                                                       const float *__restrict__ bias, float leakiness, float eps,
+                                                       float momentum, float *__restrict__ save_mean,
+                                                       float *__restrict__ save_invstd, float *__restrict__ running_mean,
+                                                       float *__restrict__ running_var) {
+    const int c0 = threadIdx.x * VEC;
+    const double dn = (double)n;
+    float sc[VEC], sh[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        const int c = c0 + e;
+        const double mean = sums[c] / dn;
+        double m2 = sums[kStatsLd + c] - mean * mean * dn;  // sum (x - mean)^2
+        if (m2 < 0.0) m2 = 0.0;
+        const float invstd = (float)(1.0 / sqrt(m2 / dn + (double)eps));
+        sc[e] = invstd * weight[c];
+        sh[e] = bias[c] - (float)mean * sc[e];
+        if (blockIdx.x == 0 && threadIdx.y == 0) {
+            save_mean[c] = (float)mean;
+            save_invstd[c] = invstd;
+            running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * (float)mean;
+            running_var[c] = momentum * running_var[c] + (1.f - momentum) * (float)(m2 / (n > 1 ? dn - 1.0 : 1.0));
+        }
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.y;
+    int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    for (; r + 3 * stride < n; r += 4 * stride) {
+        float v[4][VEC];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Vec<VEC>::get(x + (r + q * stride) * ld_x + c0, v[q]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const float y = fmaf(v[q][e], sc[e], sh[e]);
+                v[q][e] = y > 0.f ? y : y * leakiness;
+            }
+            Vec<VEC>::put(out + (r + q * stride) * ld_out + c0, v[q]);
+        }
+    }
+    for (; r < n; r += stride) {
+        float v[VEC];
+        Vec<VEC>::get(x + r * ld_x + c0, v);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const float y = fmaf(v[e], sc[e], sh[e]);
+            v[e] = y > 0.f ? y : y * leakiness;
+        }
+        Vec<VEC>::put(out + r * ld_out + c0, v);
+    }
+}
+
 struct BnShape {
     int vec;
     dim3 block;
@@ -530,7 +587,8 @@ size_t bn_workspace_bytes(int planes) { return bn_ws_floats(planes) * 4; }
 
 int bn_forward(const float *in, int64_t ld_in, float *out, int64_t ld_out, float *save_mean, float *save_invstd,
                float *running_mean, float *running_var, const float *weight, const float *bias, float eps, float momentum,
-               int train, float leakiness, int64_t n_active, int planes, void *workspace, cudaStream_t s) {
+               int train, float leakiness, int64_t n_active, int planes, void *workspace, cudaStream_t s,
+               const double *stats) {
     MOPA_CHECK(planes > 0 && planes <= 256, "BatchNormalization: planes must be in [1, 256]");
     MOPA_CHECK(weight && bias, "BatchNormalization: affine parameters are required");
     if (n_active == 0) return 0;
@@ -539,6 +597,13 @@ int bn_forward(const float *in, int64_t ld_in, float *out, int64_t ld_out, float
     MOPA_CHECK(sh.block.x * sh.block.y <= 256, "BatchNormalization: unaligned features with more than 256 planes");
     float *ws = reinterpret_cast<float *>(workspace);
     const int prof = prof_begin(40, nullptr, planes, planes, n_active, s);
+    if (train && stats && sh.vec == 4) {  // the producing convolution accumulated the column sums in its epilogue
+        k_bn_apply_sums<4><<<sh.grid, sh.block, 0, s>>>(in, ld_in, out, ld_out, n_active, planes, stats, weight, bias, leakiness,
+                                                        eps, momentum, save_mean, save_invstd, running_mean, running_var);
+        MOPA_LAUNCHED();
+        prof_end(prof, s);
+        return 0;
+    }
     if (train && sh.vec == 4 && bn_fused_enabled()) {
         const BnShapeArgs A{in, ld_in, nullptr, 0, out, ld_out, n_active, planes, ws, nullptr, nullptr, weight, bias, leakiness,
                             1, eps, momentum, save_mean, save_invstd, running_mean, running_var, nullptr, nullptr, 0};

@@ -608,7 +608,11 @@ static int dispatch_np(const Gather &gt, const float *in, int64_t ld_in, float *
 
 // out (n_out rows, c_out) = gather-conv of in with the (possibly transposed / flipped) weights
 int conv_apply(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *weight,
-               const float *packed, int n_in0, int n_out0, int transpose, int flip, int precision, cudaStream_t s) {
+               const float *packed, int n_in0, int n_out0, int transpose, int flip, int precision, cudaStream_t s,
+               double *stats, bool *stats_done) {
+    // stats: per-column sum / sum of squares of the output rows are added there IF the tcgen05 kernel runs this op
+    // (*stats_done tells the caller); the BatchNorm that follows then skips its own statistics pass
+    if (stats_done) *stats_done = false;
     if (gt.n_out == 0) return 0;
     const int c_in = transpose ? n_out0 : n_in0, c_out = transpose ? n_in0 : n_out0;
     const int prof = prof_begin((transpose ? 20 : 10) + gt.op, &gt, c_in, c_out, gt.n_out, s);
@@ -635,7 +639,10 @@ int conv_apply(const Gather &gt, const float *in, int64_t ld_in, float *out, int
     }
     const int split = precision == MOPA_SCN_PREC_FP32;
     if (!split && conv_tc_enabled() && conv_tc_supported(c_in, c_out))
-        return conv_apply_tc(gt, in, ld_in, out, ld_out, packed, c_in, c_out, s);
+    {
+        if (stats_done) *stats_done = stats != nullptr;
+        return conv_apply_tc(gt, in, ld_in, out, ld_out, packed, c_in, c_out, stats, s);
+    }
     switch (c_out / 16) {
         case 1: return dispatch_np<1>(gt, in, ld_in, out, ld_out, packed, c_in, split, s);
         case 2: return dispatch_np<2>(gt, in, ld_in, out, ld_out, packed, c_in, split, s);

@@ -39,6 +39,7 @@ constexpr int kTcThreads = 11 * 32;  // 8 gather warps, weight producer, two MMA
 constexpr int kTcChunk = 32;          // input channels per pipeline step (one 128-byte swizzle row)
 constexpr int kTcAStage = 128 * 128;  // bytes: 128 rows x 128 bytes
 constexpr int kTcMaxSA = 12, kTcMaxSB = 8;
+constexpr int kTcStatsLd = 256;      // BatchNorm statistics block of a buffer: [sum x | sum x^2], 256 doubles each
 constexpr int kTcLook = 6;          // neighbour ids are looked up this many offsets ahead
 
 __host__ __device__ inline int tc_tmem_cols(int nt, int tpc = 2) {  // power of two >= 32 holding tpc accumulators of nt columns
@@ -105,7 +106,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int nt, int sa, int sb, int na 
 template <int NA>
 __global__ void __launch_bounds__(kTcThreads, NA == 2 ? 1 : 2)  // the two-atom variant only runs one CTA per SM
     k_conv_tc(Gather gt, const float *__restrict__ in, int64_t ld_in, float *__restrict__ out, int64_t ld_out,
-              const float *__restrict__ packed, int c_in, int NT, int SA, int SB, int TPC) {
+              const float *__restrict__ packed, int c_in, int NT, int SA, int SB, int TPC, double *__restrict__ stats) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const TcSmem L = tc_smem_layout(NT, SA, SB, NA);
@@ -263,6 +264,10 @@ __global__ void __launch_bounds__(kTcThreads, NA == 2 ? 1 : 2)  // the two-atom 
             tc_fence_after_sync();
             float *dst = out + row * ld_out;
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(mt * NT);
+            // per-column sums of the output rows for the BatchNorm that follows (stats != nullptr): warp transpose-reduce,
+            // one partial per warp in shared memory (the stage ring is idle once d_full has completed), combined after
+            // the final barrier and added to the fp64 accumulators with one atomic per column and CTA
+            float *s_part = reinterpret_cast<float *>(sA) + (size_t)warp * 2 * NT;
             for (int q = 0; q < NT / 16; ++q) {
                 float v[16];
                 tmem_ld16(taddr + 16 * q, v);  // warp-collective: every lane takes part, also beyond n_out
@@ -273,6 +278,36 @@ __global__ void __launch_bounds__(kTcThreads, NA == 2 ? 1 : 2)  // the two-atom 
                         float4 *p = reinterpret_cast<float4 *>(dst + 16 * q + 4 * e);
                         if (gt.accumulate) { const float4 x = *p; o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w; }
                         *p = o;
+                    }
+                }
+                if (stats) {  // warp-uniform
+                    float a[16], b[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        a[e] = row < gt.n_out ? v[e] : 0.f;
+                        b[e] = a[e] * a[e];
+                    }
+                    // butterfly: after the steps with strides 16, 8, 4, 2 a lane holds ONE column's sum over 16 of the 32
+                    // rows (column = bits 4..1 of the lane, msb first); stride 1 adds the two halves
+#pragma unroll
+                    for (int w = 8, stride = 16; w >= 1; w >>= 1, stride >>= 1) {
+                        const bool up = lane & stride;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            if (e < w) {
+                                const float sa = up ? a[e] : a[e + w], ka = up ? a[e + w] : a[e];
+                                const float sb2 = up ? b[e] : b[e + w], kb = up ? b[e + w] : b[e];
+                                a[e] = ka + __shfl_xor_sync(0xffffffffu, sa, stride);
+                                b[e] = kb + __shfl_xor_sync(0xffffffffu, sb2, stride);
+                            }
+                        }
+                    }
+                    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+                    b[0] += __shfl_xor_sync(0xffffffffu, b[0], 1);
+                    if (!(lane & 1)) {
+                        const int col = 16 * q + (((lane >> 4) & 1) << 3) + (((lane >> 3) & 1) << 2) + (((lane >> 2) & 1) << 1) + ((lane >> 1) & 1);
+                        s_part[col] = a[0];
+                        s_part[NT + col] = b[0];
                     }
                 }
             }
@@ -340,6 +375,12 @@ __global__ void __launch_bounds__(kTcThreads, NA == 2 ? 1 : 2)  // the two-atom 
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 9) tmem_dealloc(tmem_base, tmem_cols);
+    if (stats && tid < 2 * NT) {  // [0, NT): sum x, [NT, 2 NT): sum x^2; warps of the tiles that hold rows, in order
+        const float *s_all = reinterpret_cast<const float *>(sA);
+        float sum = 0.f;
+        for (int w = 0; w < 4 * n_mt; ++w) sum += s_all[(size_t)w * 2 * NT + tid];
+        atomicAdd(stats + (tid < NT ? tid : kTcStatsLd + (tid - NT)), (double)sum);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -381,7 +422,7 @@ int pack_weights_tc_batch(TcPackJobs &jobs, int n_jobs, cudaStream_t s) {
 }
 
 int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *packed,
-                  int c_in, int c_out, cudaStream_t s) {
+                  int c_in, int c_out, double *stats, cudaStream_t s) {
     const int nt = c_out;
     // ring depths. An A stage is 16 KB but carries only the few rows that have a rule at that offset, so the gather bytes
     // in flight are set by the NUMBER of stages (kept even for two-tile CTAs: tile 0 uses the even stages, tile 1 the odd).
@@ -428,9 +469,9 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
     }
     dim3 grid((unsigned)ceil_div(gt.n_out, 128 * tpc));
     if (na == 2)
-        k_conv_tc<2><<<grid, kTcThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc);
+        k_conv_tc<2><<<grid, kTcThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc, stats);
     else
-        k_conv_tc<1><<<grid, kTcThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc);
+        k_conv_tc<1><<<grid, kTcThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc, stats);
     MOPA_LAUNCHED();
     return 0;
 }

@@ -64,7 +64,8 @@ int meta_alloc(mopa_scn_metadata *m, void **p, size_t bytes, cudaStream_t s);
 int set_locations(mopa_scn_metadata *m, int64_t spatial_size, const int64_t *coords, int64_t n, int ncols,
                   int coords_on_device, cudaStream_t s);
 int conv_apply(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *weight,
-               const float *packed, int n_in0, int n_out0, int transpose, int flip, int precision, cudaStream_t s);
+               const float *packed, int n_in0, int n_out0, int transpose, int flip, int precision, cudaStream_t s,
+               double *stats = nullptr, bool *stats_done = nullptr);
 int conv_dweight(const Gather &gt, const float *in, int64_t ld_in, const float *dout, int64_t ld_dout, float *dw,
                  int n_in, int n_out, int precision, void *workspace, size_t workspace_bytes, cudaStream_t s);
 size_t dw_workspace_bytes(int volume, int n_in, int n_out, int64_t n_rows);
@@ -91,7 +92,7 @@ struct TcPackJobs {
 int pack_weights_tc_batch(TcPackJobs &jobs, int n_jobs, cudaStream_t s);
 bool conv_packs_tc(int c_in, int c_out, int precision);  // this shape's weights go through pack_weights_tc
 int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *packed,
-                  int c_in, int c_out, cudaStream_t s);
+                  int c_in, int c_out, double *stats, cudaStream_t s);
 // tcgen05 d_weight (conv_dw_tc.cu): TF32 mode, channel counts that are multiples of 16
 bool dw_tc_enabled();
 bool dw_tc_supported(int n_in, int n_out);
@@ -103,7 +104,9 @@ Gather child_gather(const Level &fine, const Level &coarse, int op = 0);
 Gather select_gather(const Level &fine, const Level &coarse, int op = 0);
 int bn_forward(const float *in, int64_t ld_in, float *out, int64_t ld_out, float *save_mean, float *save_invstd,
                float *running_mean, float *running_var, const float *weight, const float *bias, float eps, float momentum,
-               int train, float leakiness, int64_t n_active, int planes, void *workspace, cudaStream_t s);
+               int train, float leakiness, int64_t n_active, int planes, void *workspace, cudaStream_t s,
+               const double *stats = nullptr);
+constexpr int kStatsLd = 256;  // per-buffer statistics block: [sum x | sum x^2], kStatsLd doubles each (conv epilogue -> BatchNorm)
 int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, const float *d_out, int64_t ld_dout,
                 const float *save_mean, const float *save_invstd, const float *weight, const float *bias, float *d_weight,
                 float *d_bias, float leakiness, int train, int64_t n_active, int planes, void *workspace, int accumulate,

@@ -131,6 +131,9 @@ static int make_layout(const mopa_scn_program *p, const mopa_scn_metadata *m, in
         }
     }
     L.packed_bytes += 256;
+    // forward reuses the d_weight workspace for the BatchNorm statistics blocks (one per buffer, conv epilogue -> BN)
+    const size_t stats_bytes = align256(nb * (size_t)2 * kStatsLd * sizeof(double));
+    if (stats_bytes > L.dw_bytes) L.dw_bytes = stats_bytes;
     L.act_bytes = off + 256;
     return 0;
 }
@@ -269,6 +272,26 @@ int mopa_scn_Program_forward(mopa_scn_program *p, mopa_scn_metadata *m, const fl
     Layout L;
     MOPA_TRY(make_layout(p, m, precision, L));
     MOPA_TRY(pack_all(p, L, params, precision, false, nullptr, scratch, s));
+    // BatchNorm statistics ride on the producing convolution's epilogue (tcgen05 kernel, train mode): one block of
+    // [sum x | sum x^2] per buffer, children of a joined buffer own column ranges of their parent's block
+    const char *nofuse = getenv("MOPA_SCN_NO_BNSTATS_FUSION");  // read per call (A/B measurements, bitwise eager/compiled test)
+    const bool fuse_stats = !(nofuse && nofuse[0] == '1');
+    const size_t nb = p->bufs.size();
+    double *stats_base = reinterpret_cast<double *>(reinterpret_cast<char *>(scratch) + L.packed_bytes);
+    std::vector<char> stats_ok(nb, 0);
+    const bool want_stats = train && fuse_stats;
+    if (want_stats) MOPA_CUDA(cudaMemsetAsync(stats_base, 0, nb * (size_t)2 * kStatsLd * sizeof(double), s));
+    auto stats_of = [&](int b) {
+        const PBuf &B = p->bufs[b];
+        return stats_base + (size_t)(B.parent >= 0 ? B.parent : b) * 2 * kStatsLd + (B.parent >= 0 ? B.col_off : 0);
+    };
+    auto stats_ready = [&](int b) {  // every column of buffer b has been accumulated
+        if (stats_ok[b]) return true;
+        int covered = 0, kids = 0;
+        for (size_t c = 0; c < nb; ++c)
+            if (p->bufs[c].parent == b) { ++kids; if (stats_ok[c]) covered += p->bufs[c].channels; }
+        return kids > 0 && covered == p->bufs[b].channels;
+    };
     BufView b0 = view(L, act_arena, p->in_buf);
     MOPA_TRY(mopa_scn_InputLayer_updateOutput(m, feats, ld_feats, p->in_planes, b0.ptr, b0.ld, s));
     for (size_t i = 0; i < p->ops.size(); ++i) {
@@ -279,15 +302,18 @@ int mopa_scn_Program_forward(mopa_scn_program *p, mopa_scn_metadata *m, const fl
             MOPA_TRY(bn_forward(in.ptr, in.ld, ob.ptr, ob.ld, save, save + o.n_in, (float *)params[o.param + 2],
                                 (float *)params[o.param + 3], (const float *)params[o.param],
                                 (const float *)params[o.param + 1], o.eps, o.momentum, train, o.leak,
-                                m->levels[o.level_in].V, o.n_in, p->bn_ws, s));
+                                m->levels[o.level_in].V, o.n_in, p->bn_ws, s,
+                                want_stats && stats_ready(o.in) ? stats_of(o.in) : nullptr));
             continue;
         }
-        const int volume = o.type == OP_SUBM ? 27 : 8;
         const float *w = (const float *)params[o.param];
         const float *pk = conv_uses_packed(o.n_in, o.n_out)
                               ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(scratch) + L.pk_off[i])
                               : nullptr;
-        MOPA_TRY(conv_apply(op_gather(o, m, false), in.ptr, in.ld, ob.ptr, ob.ld, w, pk, o.n_in, o.n_out, 0, 0, precision, s));
+        bool done = false;
+        MOPA_TRY(conv_apply(op_gather(o, m, false), in.ptr, in.ld, ob.ptr, ob.ld, w, pk, o.n_in, o.n_out, 0, 0, precision, s,
+                            want_stats ? stats_of(o.out) : nullptr, &done));
+        stats_ok[o.out] = done;
     }
     BufView last = view(L, act_arena, p->out_buf);
     return mopa_scn_OutputLayer_updateOutput(m, last.ptr, last.ld, p->bufs[p->out_buf].channels, out, ld_out, s);
