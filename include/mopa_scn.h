@@ -118,6 +118,11 @@ int mopa_scn_Deconvolution_updateOutput(mopa_scn_metadata *m, int64_t in_spatial
  * is OVERWRITTEN (deterministic two-stage reduction; autograd accumulates). workspace: device scratch of at least
  * mopa_scn_backwardWorkspaceBytes(...) bytes. */
 size_t mopa_scn_backwardWorkspaceBytes(int volume, int n_in, int n_out, int64_t n_rules);
+/* Host-only inspection of how the tcgen05 d_weight kernel splits `n_rows` output rows of a `volume`-offset rulebook into
+ * work items (subm_table != 0: 3x3x3 submanifold table whose centre offset carries one rule per row and is split finer).
+ * plan_out[6] = {centre offset or -1, rows per item, items per ordinary offset, rows per centre item, centre items,
+ * total items}. No device call; used by the CPU tests (every row of every offset is covered exactly once). */
+int mopa_scn_debug_dweightPlan(int volume, int subm_table, int64_t n_rows, int *plan_out);
 int mopa_scn_SubmanifoldConvolution_backward(mopa_scn_metadata *m, int64_t spatial_size, int filter_size,
                                              const float *in, int64_t ld_in, float *d_in, int64_t ld_din,
                                              const float *d_out, int64_t ld_dout, const float *weight,

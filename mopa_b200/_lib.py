@@ -44,6 +44,7 @@ PROTOTYPES = {
     "mopa_scn_Convolution_updateOutput": (_int, [_p, _i64, _i64, _int, _int, _p, _i64, _p, _i64, _p, _p, _int, _int, _int, _p]),
     "mopa_scn_Deconvolution_updateOutput": (_int, [_p, _i64, _i64, _int, _int, _p, _i64, _p, _i64, _p, _p, _int, _int, _int, _p]),
     "mopa_scn_backwardWorkspaceBytes": (_sz, [_int, _int, _int, _i64]),
+    "mopa_scn_debug_dweightPlan": (_int, [_int, _int, _i64, ctypes.POINTER(ctypes.c_int)]),
     "mopa_scn_SubmanifoldConvolution_backward": (_int, [_p, _i64, _int, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _int, _int, _int, _p, _sz, _p]),
     "mopa_scn_Convolution_backward": (_int, [_p, _i64, _i64, _int, _int, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _int, _int, _int, _p, _sz, _p]),
     "mopa_scn_Deconvolution_backward": (_int, [_p, _i64, _i64, _int, _int, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _int, _int, _int, _p, _sz, _p]),

@@ -419,3 +419,11 @@ int conv_dweight_tc(const Gather &gt, const float *in, int64_t ld_in, const floa
 }
 
 }  // namespace mopa
+
+extern "C" int mopa_scn_debug_dweightPlan(int volume, int subm_table, int64_t n_rows, int *plan_out) {
+    if (!plan_out || (volume != 27 && volume != 8) || n_rows < 0) return 1;
+    const mopa::DwTcPlan p = mopa::dw_tc_plan(volume, subm_table != 0, n_rows);
+    plan_out[0] = p.centre; plan_out[1] = p.rpi; plan_out[2] = p.n_o; plan_out[3] = p.rpi_c; plan_out[4] = p.n_c;
+    plan_out[5] = p.items;
+    return 0;
+}

@@ -14,18 +14,23 @@
 // adds nothing for them. The tensor core runs ~6x more MACs than there are rules (a lidar site has ~4 of 27 neighbours),
 // which still costs less time than the HBM floor of every layer; what is saved is all per-rule bookkeeping.
 //
-//   warps 0-3  gather  : warp w owns rows [32w, 32w+32) of each M tile (= TMEM lane quarter w). Per step (k, chunk, tile)
-//                        it reads its 32 neighbour ids (coalesced, prefetched one offset ahead), and for the rows that
-//                        have one copies 128 bytes of the neighbour's row into the A stage (UMMA K-major SWIZZLE_128B
-//                        layout) with cp.async; rows it wrote in the stage's previous use and does not rewrite are
-//                        zeroed again, so a stage is all-zero except for live rules. Up to SA-1 later steps stay in
-//                        flight before a step is fenced (fence.proxy.async) and signalled on its mbarrier.
-//   warp  4    weights : one lane streams W[k] chunks (pre-packed N x K K-major, same swizzle) by TMA bulk copy.
-//   warp  5    MMA     : one lane issues tcgen05.mma (M = 128, N = C_out, K = 8 per instruction, fp32 accumulate in
-//                        TMEM) and commits stage releases to mbarriers.
-//   epilogue           : when the last MMA has retired, warps 0-3 read their TMEM lanes (one output row per thread) and
-//                        write every output row to HBM once (optionally added to what is there).
-// Summation order is fixed (k ascending, chunks ascending, hardware order inside an MMA): results are deterministic.
+//   warps 0-7  gather  : four warps per M tile, warp w owns rows [32 (w & 3), +32) of its tile (= TMEM lane quarter w & 3).
+//                        Neighbour ids are looked up kTcLook offsets ahead (register ring). Per step (k, chunk) a warp
+//                        issues one ballot, 8 shuffles and 8 guarded cp.async (ignore-src form: the same instruction
+//                        copies a live 16-byte piece or zeroes a stale one) straight into the A stage (UMMA K-major
+//                        SWIZZLE_128B layout); which rows a stage holds from its previous use lives in registers. The
+//                        copies' completion arrives on the stage's mbarrier asynchronously (cp.async.mbarrier.arrive
+//                        .noinc): a warp never waits for data, all stages of the ring can be in flight.
+//   warp  8    weights : one lane streams W[k] chunks (pre-packed N x K K-major, same swizzle) by TMA bulk copy.
+//   warps 9,10 MMA     : one issuer warp per M tile: an elected lane issues tcgen05.mma (M = 128, N = C_out, K = 8 per
+//                        instruction, fp32 accumulate in TMEM) and commits the stage releases to mbarriers.
+//   epilogue           : when the last MMA has retired, the gather warps read their TMEM lanes (one output row per
+//                        thread) and write every output row to HBM once (optionally added to what is there); in the
+//                        forward pass of a training step they also reduce the per-column sum / sum of squares of the
+//                        rows for the BatchNorm that follows (shuffle transpose-reduce, one fp64 atomic per column and CTA).
+// Variants: one M tile per CTA on levels too small for 256-row CTAs; two 32-channel atoms per step (k_conv_tc<2>) where a
+// CTA is alone on its SM and bound by the per-step latency.
+// Summation order is fixed (k ascending, chunks ascending, hardware order inside an MMA): outputs are deterministic.
 #include <stdlib.h>
 
 #include "geometry.cuh"

@@ -93,3 +93,40 @@ def test_no_product_import_of_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+@pytest.mark.parametrize("volume,subm", [(27, 1), (27, 0), (8, 0)])
+def test_dweight_work_plan_covers_every_row_of_every_offset_once(volume, subm):
+    """Host logic of the tcgen05 d_weight kernel (csrc/conv_dw_tc.cu::dw_tc_plan): items = (offset, row range). Replays the
+    kernel's item -> (k, rows) mapping and checks that each offset's ranges tile [0, n_rows) exactly, that the centre offset
+    of a submanifold table is split finer, and that the item count (= partial slices = workspace) stays bounded."""
+    lib = _lib.load()
+    for n_rows in (0, 1, 511, 512, 513, 3624, 23110, 52447, 106203, 230925, 818488, 2_000_003):
+        plan = (ctypes.c_int * 6)()
+        assert lib.mopa_scn_debug_dweightPlan(volume, subm, n_rows, plan) == 0
+        centre, rpi, n_o, rpi_c, n_c, items = list(plan)
+        assert (centre == 13) == bool(subm and volume == 27)
+        covered = {k: [] for k in range(volume)}
+        for item in range(items):  # same arithmetic as the kernel
+            if centre >= 0:
+                if item < n_c:
+                    k, r0, r1 = centre, item * rpi_c, item * rpi_c + rpi_c
+                else:
+                    kk, j = divmod(item - n_c, n_o)
+                    k, r0, r1 = (kk if kk < centre else kk + 1), j * rpi, j * rpi + rpi
+            else:
+                k, j = divmod(item, n_o)
+                r0, r1 = j * rpi, j * rpi + rpi
+            covered[k].append((r0, min(r1, n_rows)))
+        for k, ranges in covered.items():
+            ranges.sort()
+            pos = 0
+            for r0, r1 in ranges:
+                assert r0 == pos or (r0 >= n_rows and r1 <= r0), (n_rows, k, ranges[:4])
+                pos = max(pos, r1)
+            assert pos == n_rows, (n_rows, k)
+        assert items <= 4 * 148 + 40 * volume  # ~4 items per SM, plus rounding
+        if centre >= 0 and n_rows > 4096:
+            assert rpi_c < rpi  # centre offset: one rule per row, split finer (floor of 512 rows per item) ...
+        if centre >= 0 and n_rows >= 100000:
+            assert rpi_c * 4 <= rpi  # ... at least 4x finer on the large levels
