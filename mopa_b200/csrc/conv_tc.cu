@@ -445,24 +445,16 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
     // two CTAs per SM when that helps: not when the whole grid fits one CTA per SM anyway (then the one CTA gets all stages)
     bool two = want_ctas >= 2 && tc_tmem_cols(nt, tpc) <= 256 && (nt <= 64 || tpc == 1) &&
                ceil_div(gt.n_out, 128 * tpc) > kNumSMs;
-    // three CTAs per SM for the narrow, large levels (C_out <= 32): the gather warps are issue-latency bound, so more
-    // resident warps matter more than ring depth (a 4-stage ring measured the same as a 6-stage one at two CTAs per SM)
-    static const int want_three = [] { const char *e = getenv("MOPA_TC_THREE"); return e ? atoi(e) : 0; }();
-    const bool three = want_three && two && tpc == 2 && nt <= 32 && ceil_div(gt.n_out, kTcTM) > 2 * kNumSMs;
+    // (Three CTAs per SM with a 4-stage ring were measured on the narrow, large levels: within noise of two CTAs with six
+    // stages, and the 11-warp CTA does not fit three times in the register file without spills; not kept.)
     int sa = 0;
     size_t cap = 0;
-    if (three) {
-        sb = 2;
-        sa = 4;
-        cap = (size_t)75 * 1024;
-    } else {
-        for (;;) {
-            cap = two ? (size_t)113 * 1024 : (size_t)226 * 1024;
-            sa = kTcMaxSA;
-            while (sa > 2 && (size_t)tc_smem_layout(nt, sa, sb, na).total + 1024 > cap) sa -= tpc;
-            if (!two || sa >= 4) break;
-            two = false;  // too few stages at two CTAs per SM: take the whole SM
-        }
+    for (;;) {
+        cap = two ? (size_t)113 * 1024 : (size_t)226 * 1024;
+        sa = kTcMaxSA;
+        while (sa > 2 && (size_t)tc_smem_layout(nt, sa, sb, na).total + 1024 > cap) sa -= tpc;
+        if (!two || sa >= 4) break;
+        two = false;  // too few stages at two CTAs per SM: take the whole SM
     }
     MOPA_CHECK((size_t)tc_smem_layout(nt, sa, sb, na).total + 1024 <= cap && sa >= 2, "conv_tc: shared memory layout does not fit");
     const size_t smem = (size_t)tc_smem_layout(nt, sa, sb, na).total + 1024;
