@@ -1,0 +1,99 @@
+"""CPU checks of the `sparseconvnet` module surface MoPA imports (mopa/models/scn_unet.py:4,25-30):
+constructor signatures, module nesting and therefore state_dict keys / shapes of [UPSTREAM] scn.UNet, so that the
+published xMUDA / MoPA 3D checkpoints (`net_3d.sparseModel.*`, checkpoint.py:39-87) load; error behaviour of what the path
+does not implement. Modules are plain torch.nn.Modules: building them needs no GPU."""
+import copy
+
+import pytest
+import torch
+
+
+def _expected_unet_keys(planes, reps=1):
+    """Keys of [UPSTREAM] networkArchitectures.UNet(dimension, reps, nPlanes, residual_blocks=False) restated from its
+    construction order: per level `reps` VGG blocks Sequential(BatchNormLeakyReLU, SubmanifoldConvolution); then
+    ConcatTable(Identity, Sequential(BNLeakyReLU, Convolution, U(rest), BNLeakyReLU, Deconvolution)), JoinTable, and `reps`
+    blocks on the joined planes."""
+    bn = ("weight", "bias", "running_mean", "running_var")
+
+    def block(prefix, idx, a, b, out):
+        out += [("%s%d.0.%s" % (prefix, idx, k), (a,)) for k in bn]
+        out.append(("%s%d.1.weight" % (prefix, idx), (27, 1, a, b)))
+
+    def u(prefix, pl, out):
+        idx = 0
+        for _ in range(reps):
+            block(prefix, idx, pl[0], pl[0], out)
+            idx += 1
+        if len(pl) > 1:
+            inner = "%s%d.1." % (prefix, idx)  # ConcatTable child 1 (child 0 is Identity: no parameters)
+            out += [(inner + "0." + k, (pl[0],)) for k in bn]
+            out.append((inner + "1.weight", (8, 1, pl[0], pl[1])))
+            u(inner + "2.", pl[1:], out)
+            out += [(inner + "3." + k, (pl[1],)) for k in bn]
+            out.append((inner + "4.weight", (8, 1, pl[1], pl[0])))
+            idx += 2  # ConcatTable, JoinTable
+            for i in range(reps):
+                block(prefix, idx, pl[0] * (2 if i == 0 else 1), pl[0], out)
+                idx += 1
+        return out
+
+    return u("", planes, [])
+
+
+def test_unet_scn_state_dict_matches_upstream_naming():
+    from mopa_b200.unet_scn import UNetSCN
+    net = UNetSCN(1)  # in_channels=1, m=16, 7 levels, reps=1 (xmuda.py:217-224)
+    sd = net.state_dict()
+    planes = [16 * (i + 1) for i in range(7)]
+    want = [("sparseModel.1.weight", (27, 1, 1, 16))]
+    want += [("sparseModel.2." + k, shape) for k, shape in _expected_unet_keys(planes)]
+    want += [("sparseModel.3." + k, (16,)) for k in ("weight", "bias", "running_mean", "running_var")]
+    assert [(k, tuple(v.shape)) for k, v in sd.items()] == want
+    assert sum(p.numel() for p in net.parameters()) == 2688656  # ~2.69 M
+    # a checkpoint saved from an upstream-shaped model loads strictly, also behind the `net_3d.` prefix MoPA uses
+    other = UNetSCN(1)
+    other.load_state_dict({k: torch.full_like(v, 0.5) for k, v in sd.items()}, strict=True)
+    assert all(bool((v == 0.5).all()) for v in other.state_dict().values())
+
+
+def test_module_surface_signatures_and_containers():
+    import sparseconvnet as scn  # the shim MoPA's `import sparseconvnet as scn` resolves to
+    seq = scn.Sequential()
+    assert seq.add(scn.InputLayer(3, 4096, mode=4)) is seq  # .add returns self (scn_unet.py:25-30 chains it)
+    seq.add(scn.SubmanifoldConvolution(3, 1, 16, 3, False)).add(scn.UNet(3, 1, [16, 32], False))
+    seq.add(scn.BatchNormReLU(16)).add(scn.OutputLayer(3))
+    assert len(list(seq.children())) == 5
+    for cls in ("Convolution", "Deconvolution", "BatchNormLeakyReLU", "JoinTable", "ConcatTable", "AddTable", "Identity",
+                "NetworkInNetwork", "SparseConvNetTensor"):
+        assert hasattr(scn, cls), cls
+    bn = scn.BatchNormLeakyReLU(32, leakiness=0.2)
+    assert bn.eps == 1e-4 and bn.momentum == 0.9 and bn.leakiness == 0.2  # upstream defaults (appendix A.3)
+    conv = scn.Convolution(3, 16, 32, 2, 2, False)
+    assert tuple(conv.weight.shape) == (8, 1, 16, 32)
+    assert tuple(scn.Deconvolution(3, 32, 16, 2, 2, False).weight.shape) == (8, 1, 32, 16)
+    # train / eval, deepcopy (train_xmuda_mopa.py:78) and in-place .data swaps (torch_ema) work on the module tree
+    twin = copy.deepcopy(seq).eval()
+    assert not twin.training and seq.training
+    with torch.no_grad():
+        for p in twin.parameters():
+            p.data = p.data * 0
+    assert all(float(p.abs().sum()) == 0 for p in twin.parameters())
+    assert any(float(p.abs().sum()) > 0 for p in seq.parameters())
+
+
+def test_unimplemented_features_raise():
+    import sparseconvnet as scn
+    with pytest.raises(NotImplementedError):
+        scn.SubmanifoldConvolution(3, 16, 16, 3, True)  # bias
+    with pytest.raises(NotImplementedError):
+        scn.Convolution(3, 16, 32, 3, 2, False)  # only size-2 stride-2
+    with pytest.raises(NotImplementedError):
+        scn.SubmanifoldConvolution(3, 16, 16, 5, False)  # only 3x3x3
+
+
+def test_cpu_tensors_fail_loudly():
+    """No CPU fallback: features on the host raise instead of running somewhere else."""
+    import sparseconvnet as scn
+    from mopa_b200._lib import ScnError
+    with pytest.raises(ScnError):
+        scn.InputLayer(3, 4096, mode=4)([torch.zeros(4, 4, dtype=torch.long), torch.ones(4, 1)])
