@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kDwThreads) k_dw_mma(Gather gt, const float *_
                                                        const float *__restrict__ dout, int64_t ld_dout, int n_in,
                                                        int n_out, int rows_per_chunk, int RT, int WK,
                                                        float *__restrict__ partial, int kmap_center) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     // offset order: the centre offset of a submanifold filter carries V rules (6x the others) -> schedule it first
     int k = blockIdx.y;
     if (kmap_center >= 0) k = (k == 0) ? kmap_center : (k <= kmap_center ? k - 1 : k);

@@ -233,7 +233,7 @@ int mopa_scn_Program_prepare(mopa_scn_program *p, mopa_scn_metadata *m, const in
                              int coords_on_device, int precision, void *stream, int64_t *n_active_out,
                              uint64_t *sizes_out) {
     MOPA_CHECK(p && m, "null program / metadata");
-    cudaStream_t main = (cudaStream_t)stream, gs;
+    cudaStream_t main = (cudaStream_t)stream, gs = nullptr;
     MOPA_CUDA(cudaSetDevice(m->device));
     MOPA_TRY(geom_stream(m->device, &gs));
     m->last_stream = main;
