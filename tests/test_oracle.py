@@ -139,3 +139,60 @@ def test_golden_fixture_reproduces_on_cpu():
     # float32 oracle within the fp32 bar of the GPU tests
     o32 = so.OracleUNetSCN(st).forward(z["coords"], z["feats"])
     assert float((o32.double() - out).abs().max() / out.abs().max()) < 5e-4
+
+
+# ------------------------------------------------------------------------------------------------ properties (SURVEY 8(c)(3,4))
+def test_layer_gradients_pass_gradcheck_in_float64():
+    """torch.autograd.gradcheck of the oracle's conv / strided conv / deconv / BatchNorm on a tiny grid (float64)."""
+    coords = random_cloud(40, 6, 5, n_batch=1, dup_frac=0.0)
+    geo = so.Geometry(coords, 8)
+    v0 = geo.n_active(0)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(v0, 2, dtype=torch.float64, generator=g, requires_grad=True)
+    w = torch.randn(27, 1, 2, 3, dtype=torch.float64, generator=g, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda a, b: so.submanifold_conv(geo, 0, a, b), (x, w), eps=1e-6, atol=1e-6)
+    wd = torch.randn(8, 1, 2, 3, dtype=torch.float64, generator=g, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda a, b: so.strided_conv(geo, 0, a, b), (x, wd), eps=1e-6, atol=1e-6)
+    xc = torch.randn(geo.n_active(1), 3, dtype=torch.float64, generator=g, requires_grad=True)
+    wu = torch.randn(8, 1, 3, 2, dtype=torch.float64, generator=g, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda a, b: so.strided_deconv(geo, 0, a, b), (xc, wu), eps=1e-6, atol=1e-6)
+    gam = torch.rand(2, dtype=torch.float64, generator=g).add(0.5).requires_grad_(True)
+    bet = torch.randn(2, dtype=torch.float64, generator=g, requires_grad=True)
+
+    def bn(a, ga, be):
+        return so.batchnorm_leakyrelu(a, ga, be, torch.zeros(2, dtype=torch.float64), torch.ones(2, dtype=torch.float64), True,
+                                      leakiness=0.3)
+    assert torch.autograd.gradcheck(bn, (x, gam, bet), eps=1e-6, atol=1e-5)
+
+
+def test_permuting_the_points_permutes_the_outputs():
+    """Row i of the output belongs to input point i whatever the order of the points (voxel ids change with the order, the
+    per-point result must not). float64: the summation order inside a voxel / over rules changes with the permutation."""
+    coords, feats = small_batch(2, 50, 2)
+    feats = np.random.default_rng(0).normal(size=feats.shape).astype(np.float32)
+    st = so.make_unet_state(seed=5)
+    a = so.OracleUNetSCN(st, dtype=torch.float64).forward(coords, feats)
+    perm = np.random.default_rng(1).permutation(coords.shape[0])
+    b = so.OracleUNetSCN(st, dtype=torch.float64).forward(coords[perm], feats[perm])
+    assert float((a[perm] - b).abs().max()) < 1e-9 * float(a.abs().max())
+
+
+def test_duplicate_points_get_identical_outputs_and_samples_do_not_interact():
+    coords, feats = small_batch(2, 50, 3)
+    st = so.make_unet_state(seed=6)
+    # duplicates: append copies of the first 20 points
+    c2 = np.concatenate([coords, coords[:20]], 0)
+    f2 = np.concatenate([feats, feats[:20]], 0)
+    out = so.OracleUNetSCN(st, dtype=torch.float64).forward(c2, f2, train=False)
+    assert torch.equal(out[:20], out[-20:])
+    # batch separation (eval mode: BatchNorm uses running statistics, the only cross-sample coupling is gone): a sample's
+    # rows do not change when the other sample is replaced
+    keep = coords[:, 3] == 0
+    other, _ = small_batch(1, 70, 9)
+    other = other.copy()
+    other[:, 3] = 1
+    c3 = np.concatenate([coords[keep], other], 0)
+    f3 = np.concatenate([feats[keep], np.ones((other.shape[0], 1), np.float32)], 0)
+    a = so.OracleUNetSCN(st, dtype=torch.float64).forward(coords, feats, train=False)[torch.from_numpy(keep)]
+    b = so.OracleUNetSCN(st, dtype=torch.float64).forward(c3, f3, train=False)[: int(keep.sum())]
+    assert torch.equal(a, b)
