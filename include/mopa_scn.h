@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MOPA_SCN_ABI_VERSION 1
+#define MOPA_SCN_ABI_VERSION 2
 
 /* arithmetic mode of the conv contractions (fp32 storage and fp32 accumulation in both) */
 #define MOPA_SCN_PREC_FP32 0 /* 3xTF32 split-operand MMA: fp32-equivalent products (parity mode) */
@@ -87,6 +87,16 @@ int mopa_scn_Metadata_getSubmanifoldRuleBook(mopa_scn_metadata *m, int64_t spati
 /* strided rulebook in_size -> in_size/2: counts_host[8]; pairs (n_active(in), 2) [fine, coarse], offset-major */
 int mopa_scn_Metadata_getConvolutionRuleBook(mopa_scn_metadata *m, int64_t in_spatial_size, int64_t *counts_host,
                                              int32_t *pairs_host);
+
+/* tile rulebooks (the form the tcgen05 conv kernels consume; no upstream counterpart -- upstream's kernels walk the pair
+ * lists above): for every tile of 128 output rows and filter offset k, lists_host[(t * K + k) * 128 + i], i < n(t, k), holds
+ * the tile's rules at that offset in ascending row order as in_row | (row_in_tile << 25), and masks_host[(t * K + k) * 4 ..]
+ * the 128-bit mask of the tile rows that have a rule (entries beyond n(t, k) are unspecified). kind 0: 3x3x3 submanifold
+ * at spatial_size (K = 27); kind 1: Convolution rules spatial_size -> spatial_size/2 indexed by COARSE rows (K = 8);
+ * kind 2: the same rules indexed by FINE rows (Deconvolution forward / Convolution input gradient, K = 8).
+ * tiles_out receives the tile count; pass NULL buffers to query it. */
+int mopa_scn_Metadata_getTileRuleBook(mopa_scn_metadata *m, int64_t spatial_size, int kind, int64_t *tiles_out,
+                                      int32_t *lists_host, uint32_t *masks_host);
 
 /* ---- weights: repack (volume, nIn, nOut) fp32 into the MMA fragment order the conv kernels stream -------------
  * transpose = 0: forward operand. transpose = 1: operand of the input-gradient pass (W[k]^T; for submanifold

@@ -1,7 +1,9 @@
 """Builds libmopa_scn.so (sm_100a only) in-tree with nvcc. No torch dependency: the library is plain CUDA + C ABI."""
+import fcntl
 import os
 import shutil
 import subprocess
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -27,27 +29,48 @@ def stale():
 
 
 def build(force=False, verbose=False):
+    """Compile + link under an exclusive file lock (torchrun starts one process per GPU on the same checkout: only one
+    of them builds, the others wait and find a fresh library). Objects and the library are written under temporary names
+    and moved into place with os.replace, so a concurrent dlopen never sees a half-written file."""
     if not force and not stale():
         return LIB
-    objs = []
-    procs = []
-    for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-               "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        for d in os.environ.get("MOPA_BUILD_DEFS", "").split():  # e.g. MOPA_TC_TRACE (debug timeline in conv_tc.cu)
-            cmd.insert(1, "-D" + d)
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
-    for src, p in procs:
-        out, _ = p.communicate()
-        if verbose or p.returncode:
-            print(out)
-        if p.returncode:
-            raise RuntimeError("nvcc failed on %s" % src)
-    subprocess.check_call([_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not stale():  # another process built it while we waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
+    tmpdir = tempfile.mkdtemp(prefix=".build-", dir=HERE)
+    try:
+        tmp_objs, procs = [], []
+        for src in SOURCES:
+            obj = os.path.join(tmpdir, src.replace(".cu", ".o"))
+            cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+                   "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            for d in os.environ.get("MOPA_BUILD_DEFS", "").split():  # e.g. MOPA_TC_TRACE (debug timeline in conv_tc.cu)
+                cmd.insert(1, "-D" + d)
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+            tmp_objs.append(obj)
+        for src, p in procs:
+            out, _ = p.communicate()
+            if verbose or p.returncode:
+                print(out)
+            if p.returncode:
+                raise RuntimeError("nvcc failed on %s" % src)
+        tmp_lib = os.path.join(tmpdir, "libmopa_scn.so")
+        subprocess.check_call([_nvcc(), "-shared", "-o", tmp_lib] + tmp_objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+        for obj in tmp_objs:  # keep the objects beside the sources (cuobjdump / -res-usage inspection)
+            os.replace(obj, os.path.join(CSRC, os.path.basename(obj)))
+        os.replace(tmp_lib, LIB)
+    finally:
+        shutil.rmtree(tmpdir, ignore_errors=True)
     return LIB
 
 

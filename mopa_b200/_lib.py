@@ -5,6 +5,7 @@ are the single source of truth for the Python side; tests/test_abi.py checks the
 """
 import ctypes
 import os
+import warnings
 
 from . import _build
 
@@ -17,6 +18,7 @@ _sz = _c.c_size_t
 
 PREC_FP32 = 0
 PREC_TF32 = 1
+ABI_VERSION = 2  # MOPA_SCN_ABI_VERSION in include/mopa_scn.h
 
 # name -> (restype, argtypes); order and types mirror include/mopa_scn.h
 PROTOTYPES = {
@@ -38,6 +40,7 @@ PROTOTYPES = {
     "mopa_scn_Metadata_getInputRules": (_int, [_p, _p, _p]),
     "mopa_scn_Metadata_getSubmanifoldRuleBook": (_int, [_p, _i64, _p, _p]),
     "mopa_scn_Metadata_getConvolutionRuleBook": (_int, [_p, _i64, _p, _p]),
+    "mopa_scn_Metadata_getTileRuleBook": (_int, [_p, _i64, _int, _c.POINTER(_i64), _p, _p]),
     "mopa_scn_packedWeightFloats": (_i64, [_int, _int, _int, _int]),
     "mopa_scn_packWeights": (_int, [_p, _int, _int, _int, _int, _int, _int, _p, _p]),
     "mopa_scn_SubmanifoldConvolution_updateOutput": (_int, [_p, _i64, _int, _p, _i64, _p, _i64, _p, _p, _int, _int, _int, _p]),
@@ -76,6 +79,14 @@ class ScnError(RuntimeError):
     pass
 
 
+def _nvcc_present():
+    try:
+        _build._nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
 def library_path():
     return _build.LIB
 
@@ -88,17 +99,23 @@ def load():
     path = _build.LIB
     if not os.path.exists(path) or _build.stale():
         try:
-            _build.build()
-        except Exception as e:  # no nvcc on this box and no prebuilt library
+            _build.build()  # takes a file lock: one builder per checkout, atomic replace of the .so
+        except Exception as e:  # no nvcc on this box, or the sources do not compile
             if not os.path.exists(path):
                 raise ScnError("libmopa_scn.so is missing and could not be built (%s); mopa_b200 has no CPU fallback" % e)
+            if os.environ.get("MOPA_SCN_ALLOW_STALE") != "1" and _nvcc_present():
+                raise ScnError("libmopa_scn.so is older than its sources and the rebuild failed (%s); set "
+                               "MOPA_SCN_ALLOW_STALE=1 to load the old binary anyway" % e)
+            warnings.warn("libmopa_scn.so is older than its sources and could not be rebuilt (%s): loading the existing "
+                          "binary" % e, RuntimeWarning)
     lib = _c.CDLL(path)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.mopa_scn_abi_version() != 1:
-        raise ScnError("libmopa_scn.so ABI version mismatch")
+    if lib.mopa_scn_abi_version() != ABI_VERSION:
+        raise ScnError("libmopa_scn.so reports ABI version %d, this binding was written for %d: rebuild the library"
+                       % (lib.mopa_scn_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 

@@ -11,7 +11,6 @@
 namespace mopa {
 
 // ------------------------------------------------------------------------------------------------ BatchNorm
-constexpr int kBnMaxBlocks = 4 * kNumSMs;
 constexpr int kBnMaxPlanes = 256;
 // workspace layout (floats): [0] block counter (int), [8 .. 8+2C) gradMean / k of the backward pass,
 // [8 + 512 ...) 2C fp64 accumulators (8-byte aligned). Zero between calls.
@@ -482,7 +481,8 @@ static BnShape bn_shape(int64_t n, int planes, bool vec_ok) {
     if (ty > 64) ty = 64;
     s.block = dim3(tx, ty);
     int64_t want = ceil_div(n > 0 ? n : 1, (int64_t)ty * 4);  // >= 4 rows per thread
-    s.grid = (unsigned)(want < 1 ? 1 : (want > kBnMaxBlocks ? kBnMaxBlocks : want));
+    const int64_t cap = 4 * (int64_t)num_sms();
+    s.grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
     s.smem = (size_t)ty * 2 * planes * 4;
     return s;
 }
@@ -500,15 +500,18 @@ static int launch_bn_fused(const BnShapeArgs &A, cudaStream_t s) {
     if (ty > 64) ty = 64;
     const size_t smem = (size_t)ty * 2 * A.planes * 4;
     auto kern = k_bn_fused<VEC, BWD>;
-    static int max_blocks = 0;  // per instantiation
+    static std::atomic<int> blocks_of[64];  // per instantiation and device: co-resident blocks of a cooperative launch
+    int dev = 0;
+    MOPA_CUDA(cudaGetDevice(&dev));
+    MOPA_CHECK(dev >= 0 && dev < 64, "device index out of range");
+    int max_blocks = blocks_of[dev].load(std::memory_order_relaxed);
     if (max_blocks == 0) {
-        int dev = 0, sms = 0, occ = 0;
-        MOPA_CUDA(cudaGetDevice(&dev));
-        MOPA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        int occ = 0;
         MOPA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 16 * 1024));
         if (occ > 2) occ = 2;  // (4 blocks per SM measured slower: the grid barrier and the 2C atomics per block grow)
-        MOPA_CHECK(occ >= 1 && sms >= 1, "BatchNormalization: the fused kernel does not fit on this device");
-        max_blocks = occ * sms;
+        MOPA_CHECK(occ >= 1, "BatchNormalization: the fused kernel does not fit on this device");
+        max_blocks = occ * num_sms();
+        blocks_of[dev].store(max_blocks, std::memory_order_relaxed);
     }
     int64_t want = ceil_div(A.n, (int64_t)ty * 8);  // >= 8 rows per thread
     if (want < 1) want = 1;

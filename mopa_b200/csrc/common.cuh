@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 
 namespace mopa {
@@ -42,7 +43,37 @@ inline int fail(const char *file, int line, const std::string &msg) {
             return ::mopa::fail(__FILE__, __LINE__, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
     } while (0)
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kNumSMs = 148;  // B200; used where a work plan must be reproducible without a device (d_weight items)
+
+// SM count of the CURRENT device (cached per device index); falls back to kNumSMs if the query fails
+inline int num_sms() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kNumSMs;
+        cache[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+// Function attributes (cudaFuncSetAttribute) are per DEVICE: `fn` runs once per device index, under a lock, so a second
+// GPU used by the same process (Metadata_new(device) / Program_new(..., device)) gets configured too.
+template <class F>
+inline int once_per_device(std::atomic<uint64_t> &done, F &&fn) {
+    int dev = 0;
+    MOPA_CUDA(cudaGetDevice(&dev));
+    MOPA_CHECK(dev >= 0 && dev < 64, "device index out of range");
+    const uint64_t bit = 1ull << dev;
+    if (done.load(std::memory_order_acquire) & bit) return 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.load(std::memory_order_acquire) & bit) return 0;
+    MOPA_TRY(fn());
+    done.fetch_or(bit, std::memory_order_release);
+    return 0;
+}
 
 // ---- optional per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream around the main kernel
 // of each op; off by default and free when off. tag = 10 * class + op, class 1 conv forward, 2 conv d_input,

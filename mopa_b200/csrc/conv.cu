@@ -584,12 +584,12 @@ static int launch_gather_mma(const Gather &gt, const float *in, int64_t ld_in, f
     if (stages > nsteps_max) stages = nsteps_max < 1 ? 1 : nsteps_max;
     const size_t smem = stages * stage + fixed;
     auto kern = k_gather_mma<MT, NP, SPLIT>;
-    static bool configured = false;  // per template instantiation
-    if (!configured) {
+    static std::atomic<uint64_t> configured{0};  // per template instantiation, one bit per device
+    MOPA_TRY(once_per_device(configured, [&] {
         MOPA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         MOPA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        configured = true;
-    }
+        return 0;
+    }));
     const unsigned grid = (unsigned)ceil_div(gt.n_out, TM);
     kern<<<grid, kConvThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, stages);
     MOPA_LAUNCHED();
@@ -698,12 +698,12 @@ static int launch_dw(const Gather &gt, const float *in, int64_t ld_in, const flo
                      int n_out, const DwPlan &p, float *partial, int center, cudaStream_t s) {
     const size_t smem = (size_t)(2 * kDwSub + 16) * 4 + (size_t)2 * p.RT * (n_in + 8 + n_out + 8) * 4;
     auto kern = k_dw_mma<BPW, SPLIT>;
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<uint64_t> configured{0};
+    MOPA_TRY(once_per_device(configured, [&] {
         MOPA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         MOPA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        configured = true;
-    }
+        return 0;
+    }));
     dim3 grid(p.nchunks, gt.volume);
     kern<<<grid, kDwThreads, smem, s>>>(gt, in, ld_in, dout, ld_dout, n_in, n_out, p.rows_per_chunk, p.RT, p.WK, partial,
                                         center);
@@ -782,18 +782,21 @@ int pack_weights(const float *weight, int volume, int n_in, int n_out, int trans
 Gather subm_gather(const Level &L) {
     Gather g;
     g.table = L.nbr; g.ld = L.nbr_ld; g.volume = 27; g.n_out = L.V; g.n_in = L.V; g.op = 1;
+    g.tl = L.tl_subm; g.tm = L.tm_subm;
     return g;
 }
 Gather child_gather(const Level &fine, const Level &coarse, int op) {  // rows = coarse sites, inputs = fine sites
     Gather g;
     g.op = op;
     g.table = fine.child; g.ld = fine.child_ld; g.volume = 8; g.n_out = coarse.V; g.n_in = fine.V;
+    g.tl = fine.tl_child; g.tm = fine.tm_child;
     return g;
 }
 Gather select_gather(const Level &fine, const Level &coarse, int op) {  // rows = fine sites, inputs = coarse sites
     Gather g;
     g.op = op;
     g.parent = fine.parent; g.kidx = fine.kidx; g.volume = 8; g.n_out = fine.V; g.n_in = coarse.V;
+    g.tl = fine.tl_sel; g.tm = fine.tm_sel;
     return g;
 }
 

@@ -35,10 +35,10 @@ namespace mopa {
 
 constexpr int kDwTcThreads = 5 * 32;
 constexpr int kDwTcTile = 32;    // rules per stage
-constexpr int kDwTcSub = 512;    // rows looked up per producer pass (4 per thread)
-constexpr int kDwTcList = 1024;  // pending-rule ring (entries); holds < 32 + 512
+constexpr int kDwTcSub = 512;    // granularity of an item's row range (a multiple of the 128-row rulebook tiles)
+constexpr int kDwTcMaxTiles = 2048;  // rulebook tiles per item (prefix counts in shared memory); caps rows per item
+constexpr int kDwTcList = kDwTcMaxTiles / 2 + 4;  // 8-byte slots of the prefix block (kDwTcMaxTiles + 1 ints)
 constexpr int kDwTcMaxStages = 12;
-constexpr int kDwTcLook = 3;    // producer passes of table lookups in flight
 
 struct DwTcPlan {
     int centre;  // 13 for a submanifold table, -1 otherwise
@@ -56,6 +56,7 @@ __host__ __device__ inline DwTcPlan dw_tc_plan(int volume, bool subm_table, int6
     const int groups = p.centre >= 0 ? 26 + 8 : volume;
     int64_t rpi = round_up(ceil_div(rows * groups, target), kDwTcSub);
     if (rpi < 1024) rpi = 1024;
+    if (rpi > (int64_t)(kDwTcMaxTiles - 1) * 128) rpi = (int64_t)(kDwTcMaxTiles - 1) * 128;  // prefix block of the kernel
     p.rpi = (int)rpi;
     p.n_o = (int)ceil_div(rows, rpi);
     if (p.centre >= 0) {
@@ -168,20 +169,12 @@ __global__ void __launch_bounds__(kDwTcThreads)
         const char *src_m_c = reinterpret_cast<const char *>(src_m) + 16 * sub4;
         const char *src_n_c = reinterpret_cast<const char *>(src_n) + 16 * sub4;
         const uint32_t ldm_b = (uint32_t)ld_m * 4, ldn_b = (uint32_t)ld_n * 4;
-        const uint32_t lt_mask = (1u << lane) - 1;
         int st = 0;
         uint32_t ph = 1;
-        int head = 0, tail = 0;  // pending ring: [head, tail) (uniform over the 128 producer threads)
 
-        auto emit = [&](int count, uint32_t last) {
+        auto emit = [&](uint32_t m_row, uint32_t n_row, uint32_t pad, uint32_t last) {
+            // pad: this thread's rule slot lies beyond the end of the item: zero rows (ignore-src), rows 0 are never read
             mbar_wait_s(empty_a + 8 * st, ph);
-            const uint32_t pad = rt < count ? 0u : 1u;  // rules beyond the end of the item: zero rows (ignore-src)
-            uint32_t m_row = 0, n_row = 0;
-            if (!pad) {
-                const uint32_t e = list_a + (uint32_t)((head + rt) & (kDwTcList - 1)) * 8;
-                m_row = lds_u32(e);
-                n_row = lds_u32(e + 4);
-            }
             // 32-bit row offsets (a feature matrix is far below 4 GB); this thread copies pieces sub4 and sub4 + 4 of every
             // 32-channel atom: their swizzled offsets (off0, off1) do not depend on the atom
             const char *gm = src_m_c + (uint64_t)m_row * (uint64_t)ldm_b;
@@ -207,68 +200,66 @@ __global__ void __launch_bounds__(kDwTcThreads)
             if (++st == stages) { st = 0; ph ^= 1; }
         };
 
-        // table lookups run kDwTcLook passes ahead of their use (register ring with static indices): a pass is shorter
-        // than an L2/HBM round trip
-        int vq[kDwTcLook][4];
-        auto look = [&](int64_t sub, int (&dst)[4]) {
+        // The item's rules come straight from the tile rulebook (geometry.cu::k_tile_lists): per tile of 128 output rows a
+        // compact, row-ordered list of this offset's rules. The producers first put the running rule counts of the item's
+        // tiles into shared memory; rule g of the item is then entry g - prefix[j] of tile j, and because a thread's g grows
+        // by 32 per stage it finds j with a running pointer. No table lookups, ballots or block barriers per pass.
+        const int K = gt.volume;
+        const int64_t t0 = r_begin >> 7;
+        const int ntile = r_end > r_begin ? (int)(((r_end + 127) >> 7) - t0) : 0;  // <= kDwTcMaxTiles (dw_tc_plan)
+        const uint32_t pre_a = list_a;  // prefix[0 .. ntile] (int32), in the block that used to hold the pending-rule ring
+        {
+            constexpr int PER = kDwTcMaxTiles / 128;  // tiles per thread
+            int c[PER], sum = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int64_t row = sub + q * 128 + tid;
-                dst[q] = row < r_end ? gather_lookup(gt, k, row) : -1;
+            for (int i = 0; i < PER; ++i) {
+                const int t = tid * PER + i;
+                c[i] = 0;
+                if (t < ntile) {
+                    const uint4 m = __ldg(gt.tm + (t0 + t) * K + k);
+                    c[i] = __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);
+                }
+                sum += c[i];
             }
-        };
+            int incl = sum;  // inclusive scan over the 128 producer threads: shuffles inside a warp, warp totals through smem
 #pragma unroll
-        for (int u = 0; u < kDwTcLook; ++u) look(r_begin + (int64_t)u * kDwTcSub, vq[u]);
-        auto pass = [&](int64_t sub, const int (&v)[4]) {
-            uint32_t m[4];
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (lane == 31) sts_u32(cnt_a + 4 * warp, (uint32_t)incl);
+            named_barrier_sync(1, 128);
+            int run = incl - sum;
+            for (int w = 0; w < warp; ++w) run += (int)lds_u32(cnt_a + 4 * w);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                m[q] = __ballot_sync(0xffffffffu, v[q] >= 0);
-                if (lane == 0) sts_u32(cnt_a + 4 * (q * 4 + warp), (uint32_t)__popc(m[q]));
+            for (int i = 0; i < PER; ++i) {
+                const int t = tid * PER + i;
+                if (t <= ntile) sts_u32(pre_a + 4 * t, (uint32_t)run);  // t == ntile: the item's rule count
+                run += c[i];
             }
             named_barrier_sync(1, 128);
-            int run = 0, base[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 c4 = lds_v4(cnt_a + 16 * q);
-                const int c[4] = {__float_as_int(c4.x), __float_as_int(c4.y), __float_as_int(c4.z), __float_as_int(c4.w)};
-                base[q] = run;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    if (w < warp) base[q] += c[w];
-                    run += c[w];
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (v[q] >= 0) {
-                    const int pos = tail + base[q] + __popc(m[q] & lt_mask);
-                    const int orow = (int)(sub + q * 128 + tid);  // the rule's output row; v = its input row
-                    const uint32_t e = list_a + (uint32_t)(pos & (kDwTcList - 1)) * 8;
-                    sts_u32(e, (uint32_t)(swap ? orow : v[q]));
-                    sts_u32(e + 4, (uint32_t)(swap ? v[q] : orow));
-                }
-            tail += run;
-            named_barrier_sync(1, 128);
-            while (tail - head >= kDwTcTile) {
-                emit(kDwTcTile, 0u);
-                head += kDwTcTile;
-            }
-        };
-        for (int64_t sub0 = r_begin; sub0 < r_end; sub0 += (int64_t)kDwTcLook * kDwTcSub) {
-#pragma unroll
-            for (int u = 0; u < kDwTcLook; ++u) {
-                const int64_t sub = sub0 + (int64_t)u * kDwTcSub;
-                if (sub < r_end) {  // uniform over the producers
-                    int v[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = vq[u][q];
-                    look(sub + (int64_t)kDwTcLook * kDwTcSub, vq[u]);
-                    pass(sub, v);
-                }
-            }
         }
-        emit(tail - head, 1u);  // always: carries the "last" flag (and initialises the accumulator of an empty item)
+        const int n_rules = ntile > 0 ? (int)lds_u32(pre_a + 4 * ntile) : 0;
+        const int n_stage = n_rules > 0 ? (n_rules + kDwTcTile - 1) / kDwTcTile : 1;  // an empty item still zeroes its slice
+        const int32_t *tl_k = gt.tl + ((t0 * K + k) << 7);
+        int j = 0;  // running tile pointer of this thread
+        auto locate = [&](int g, int &tile) -> int {  // list entry of rule g (g < n_rules)
+            while (g >= (int)lds_u32(pre_a + 4 * (j + 1))) ++j;
+            tile = j;
+            return __ldg(tl_k + (((int64_t)j * K) << 7) + (g - (int)lds_u32(pre_a + 4 * j)));
+        };
+        int g = rt, t_cur = 0, e_cur = 0;
+        if (g < n_rules) e_cur = locate(g, t_cur);
+        for (int sidx = 0; sidx < n_stage; ++sidx) {
+            int t_nxt = 0, e_nxt = 0;
+            if (g + kDwTcTile < n_rules) e_nxt = locate(g + kDwTcTile, t_nxt);  // next stage's entry is in flight during this one
+            const uint32_t in_row = (uint32_t)e_cur & ((1u << kTileRowShift) - 1u);
+            const uint32_t out_row = (uint32_t)((t0 + t_cur) << 7) + ((uint32_t)e_cur >> kTileRowShift);
+            emit(swap ? out_row : in_row, swap ? in_row : out_row, g < n_rules ? 0u : 1u, sidx == n_stage - 1 ? 1u : 0u);
+            g += kDwTcTile;
+            t_cur = t_nxt;
+            e_cur = e_nxt;
+        }
 
         // ================================================================= epilogue: TMEM -> partial slice
         mbar_wait(d_full, 0);
@@ -404,11 +395,11 @@ int conv_dweight_tc(const Gather &gt, const float *in, int64_t ld_in, const floa
         }
     }
     const size_t smem = (size_t)dw_tc_smem(n_ma, n_na, stages).total + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<uint64_t> configured{0};
+    MOPA_TRY(once_per_device(configured, [] {
         MOPA_CUDA(cudaFuncSetAttribute(k_dw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
-    }
+        return 0;
+    }));
     k_dw_tc<<<(unsigned)plan.items, kDwTcThreads, smem, s>>>(gt, in, ld_in, dout, ld_dout, n_in, n_out, swap, plan, stages,
                                                            partial);
     MOPA_LAUNCHED();

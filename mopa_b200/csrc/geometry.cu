@@ -56,7 +56,7 @@ int prof_begin(int tag, const Gather *gt, int c_in, int c_out, int64_t rows, cud
         r.rules = gt->table && gt->volume == 8 ? gt->n_in : gt->n_out;  // strided: one rule per fine site
         if (gt->table && gt->volume == 27 && gt->n_out > 0 && g_prof_counts) {  // submanifold: count the table's rules
             r.count_slot = (int)g_prof.size();
-            k_count_valid<<<kNumSMs * 4, 256, 0, s>>>(gt->table, gt->ld, gt->n_out, 27, g_prof_counts + r.count_slot);
+            k_count_valid<<<num_sms() * 4, 256, 0, s>>>(gt->table, gt->ld, gt->n_out, 27, g_prof_counts + r.count_slot);
         }
     }
     if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
@@ -375,6 +375,40 @@ __global__ void __launch_bounds__(256) k_child_scatter(const int32_t *__restrict
     child[(int64_t)kidx[c] * ld + parent[c]] = (int32_t)c;
 }
 
+// ------------------------------------------------------------------------------------------------ tile rulebooks
+// grid (tiles of 128 output rows, K), 128 threads: thread r looks up the input row of (offset k, output row 128 t + r) in
+// the dense table (or the select pair), the block compacts the hits in row order (ballot + popc ranks) and writes
+// the row mask. This is the warp-cooperative rulebook build the conv kernels consume: they never ballot / compact.
+__global__ void __launch_bounds__(128) k_tile_lists(const int32_t *__restrict__ table, int64_t ld,
+                                                    const int32_t *__restrict__ parent, const int32_t *__restrict__ kidx,
+                                                    int64_t V, int K, int32_t *__restrict__ tl, uint4 *__restrict__ tm) {
+    __shared__ uint32_t wm[4];
+    const int r = threadIdx.x, lane = r & 31, warp = r >> 5, k = blockIdx.y;
+    const int64_t t = blockIdx.x, o = t * kTileRows + r;
+    int id = -1;
+    if (o < V) id = table ? __ldg(table + (int64_t)k * ld + o) : (__ldg(kidx + o) == k ? __ldg(parent + o) : -1);
+    const uint32_t m = __ballot_sync(0xffffffffu, id >= 0);
+    if (lane == 0) wm[warp] = m;
+    __syncthreads();
+    int rank = __popc(m & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; ++w) rank += __popc(wm[w]);
+    const int64_t slot = t * K + k;
+    if (id >= 0) tl[(slot << 7) + rank] = id | (r << kTileRowShift);
+    if (r == 0) tm[slot] = make_uint4(wm[0], wm[1], wm[2], wm[3]);
+}
+
+static int build_tile_lists(mopa_scn_metadata *m, const int32_t *table, int64_t ld, const int32_t *parent,
+                            const int32_t *kidx, int64_t V, int64_t n_in, int K, int32_t **tl, uint4 **tm, cudaStream_t s) {
+    MOPA_CHECK(n_in < ((int64_t)1 << kTileRowShift), "more than 2^25 active sites at one level: tile rulebook entries overflow");
+    const int64_t tiles = ceil_div(V > 0 ? V : 1, kTileRows);
+    MOPA_TRY(meta_alloc(m, (void **)tl, (size_t)tiles * K * kTileRows * 4, s));
+    MOPA_TRY(meta_alloc(m, (void **)tm, (size_t)tiles * K * sizeof(uint4), s));
+    dim3 grid((unsigned)tiles, (unsigned)K);
+    k_tile_lists<<<grid, 128, 0, s>>>(table, ld, parent, kidx, V, K, *tl, *tm);
+    MOPA_LAUNCHED();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ rulebook compaction
 // Warp-cooperative ordered compaction of a dense (K, ld) table into offset-major (in, out) pairs, ascending out row.
 __global__ void __launch_bounds__(1024) k_rule_flags(const int32_t *__restrict__ table, int64_t ld, int64_t V, int K,
@@ -412,7 +446,7 @@ int ensure_subm(mopa_scn_metadata *m, int level, cudaStream_t s) {
         k_subm_table<<<grid, 256, 0, s>>>(L.keys, L.V, (int)L.spatial, L.tab_keys, L.tab_vals, L.cap - 1, L.nbr, L.nbr_ld);
         MOPA_LAUNCHED();
     }
-    return 0;
+    return build_tile_lists(m, L.nbr, L.nbr_ld, nullptr, nullptr, L.V, L.V, 27, &L.tl_subm, &L.tm_subm, s);
 }
 
 static int read_back(mopa_scn_metadata *m, const int32_t *dev, int n_ints, cudaStream_t s) {
@@ -450,6 +484,8 @@ int ensure_down(mopa_scn_metadata *m, int level, cudaStream_t s) {
         k_child_scatter<<<(unsigned)ceil_div(Vf, 256), 256, 0, s>>>(L.parent, L.kidx, Vf, L.child, L.child_ld);
         MOPA_LAUNCHED();
     }
+    MOPA_TRY(build_tile_lists(m, L.child, L.child_ld, nullptr, nullptr, N.V, Vf, 8, &L.tl_child, &L.tm_child, s));
+    MOPA_TRY(build_tile_lists(m, nullptr, 0, L.parent, L.kidx, Vf, N.V, 8, &L.tl_sel, &L.tm_sel, s));
     L.has_down = true;
     return 0;
 }
@@ -730,6 +766,27 @@ int mopa_scn_Metadata_getSubmanifoldRuleBook(mopa_scn_metadata *m, int64_t spati
     MOPA_TRY(ensure_subm(m, l, m->last_stream));
     const Level &L = m->levels[l];
     return rulebook_to_host(m, L.nbr, L.nbr_ld, L.V, 27, counts_host, pairs_host, m->last_stream);
+}
+
+int mopa_scn_Metadata_getTileRuleBook(mopa_scn_metadata *m, int64_t spatial_size, int kind, int64_t *tiles_out,
+                                      int32_t *lists_host, uint32_t *masks_host) {
+    MOPA_CHECK(m != nullptr && kind >= 0 && kind <= 2, "getTileRuleBook: bad arguments");
+    int l = m->level_of(spatial_size);
+    MOPA_CHECK(l >= 0, "no grid at this spatial size");
+    MOPA_CUDA(cudaSetDevice(m->device));
+    if (kind == 0) MOPA_TRY(ensure_subm(m, l, m->last_stream));
+    else MOPA_TRY(ensure_down(m, l, m->last_stream));
+    const Level &L = m->levels[l];
+    const int K = kind == 0 ? 27 : 8;
+    const int64_t rows = kind == 1 ? m->levels[l + 1].V : L.V;
+    const int64_t tiles = ceil_div(rows > 0 ? rows : 1, kTileRows);
+    if (tiles_out) *tiles_out = tiles;
+    const int32_t *tl = kind == 0 ? L.tl_subm : (kind == 1 ? L.tl_child : L.tl_sel);
+    const uint4 *tm = kind == 0 ? L.tm_subm : (kind == 1 ? L.tm_child : L.tm_sel);
+    MOPA_CUDA(cudaStreamSynchronize(m->last_stream));
+    if (lists_host) MOPA_CUDA(cudaMemcpy(lists_host, tl, (size_t)tiles * K * kTileRows * 4, cudaMemcpyDeviceToHost));
+    if (masks_host) MOPA_CUDA(cudaMemcpy(masks_host, tm, (size_t)tiles * K * 16, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int mopa_scn_Metadata_getConvolutionRuleBook(mopa_scn_metadata *m, int64_t in_spatial_size, int64_t *counts_host,

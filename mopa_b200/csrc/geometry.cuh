@@ -22,7 +22,18 @@ struct Level {
     int32_t *kidx = nullptr;    // [V] (x&1)*4 + (y&1)*2 + (z&1)
     int32_t *child = nullptr;   // [8 * child_ld] fine id or -1, indexed by coarse id
     int64_t child_ld = 0;
+    // tile rulebooks (what the tcgen05 conv kernel reads): for every 128-row tile t of the OUTPUT rows and offset k,
+    //   tl[(t * K + k) * 128 + i], i < n(t, k): the tile's rules at that offset, ascending row: in_row | row_in_tile << 25
+    //   tm[t * K + k]: 128-bit mask of the tile rows that have a rule at offset k (n = its popcount)
+    int32_t *tl_subm = nullptr;   // rows = this level's sites, K = 27 (from nbr)
+    uint4 *tm_subm = nullptr;
+    int32_t *tl_child = nullptr;  // rows = the NEXT (coarser) level's sites, K = 8, inputs = this level's sites (from child)
+    uint4 *tm_child = nullptr;
+    int32_t *tl_sel = nullptr;    // rows = this level's sites, K = 8, inputs = the next level's sites (from parent / kidx)
+    uint4 *tm_sel = nullptr;
 };
+constexpr int kTileRows = 128;
+constexpr int kTileRowShift = 25;  // in_row < 2^25 (checked when the lists are built)
 
 }  // namespace mopa
 
@@ -56,6 +67,8 @@ struct Gather {
     int volume = 0;     // 27 or 8
     int64_t n_out = 0;  // output rows
     int64_t n_in = 0;   // input rows (for bounds/debug)
+    const int32_t *tl = nullptr;  // tile rulebook of the same rules (see Level), always present for library-built gathers
+    const uint4 *tm = nullptr;
     int accumulate = 0; // conv_apply: add to the existing output rows instead of overwriting them
     int op = 0;         // 1 submanifold, 2 convolution, 3 deconvolution (profiling tag only)
 };

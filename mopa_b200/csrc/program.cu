@@ -112,6 +112,8 @@ static int make_layout(const mopa_scn_program *p, const mopa_scn_metadata *m, in
         L.buf_off[b] = L.buf_off[B.parent] + (size_t)B.col_off * 4;
     }
     L.grad_bytes = off + 256;
+    for (const POp &o : p->ops)  // fail up front, not in the middle of a pass (MODEL_3D.SCN.m >= 22 reaches 12 m > 256 planes)
+        MOPA_CHECK(o.type != OP_BN || (o.n_in >= 1 && o.n_in <= 256), "BatchNormalization over more than 256 planes is not supported");
     L.bn_off.assign(p->ops.size(), 0);
     L.pk_off.assign(p->ops.size(), 0);
     L.packed_bytes = 0;
@@ -281,9 +283,11 @@ int mopa_scn_Program_forward(mopa_scn_program *p, mopa_scn_metadata *m, const fl
     std::vector<char> stats_ok(nb, 0);
     const bool want_stats = train && fuse_stats;
     if (want_stats) MOPA_CUDA(cudaMemsetAsync(stats_base, 0, nb * (size_t)2 * kStatsLd * sizeof(double), s));
-    auto stats_of = [&](int b) {
+    auto stats_of = [&](int b) -> double * {  // nullptr: the (joined) buffer is wider than a statistics block
         const PBuf &B = p->bufs[b];
-        return stats_base + (size_t)(B.parent >= 0 ? B.parent : b) * 2 * kStatsLd + (B.parent >= 0 ? B.col_off : 0);
+        const int root = B.parent >= 0 ? B.parent : b;
+        if (p->bufs[root].channels > kStatsLd) return nullptr;
+        return stats_base + (size_t)root * 2 * kStatsLd + (B.parent >= 0 ? B.col_off : 0);
     };
     auto stats_ready = [&](int b) {  // every column of buffer b has been accumulated
         if (stats_ok[b]) return true;
@@ -311,9 +315,10 @@ int mopa_scn_Program_forward(mopa_scn_program *p, mopa_scn_metadata *m, const fl
                               ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(scratch) + L.pk_off[i])
                               : nullptr;
         bool done = false;
+        double *st_out = want_stats ? stats_of(o.out) : nullptr;
         MOPA_TRY(conv_apply(op_gather(o, m, false), in.ptr, in.ld, ob.ptr, ob.ld, w, pk, o.n_in, o.n_out, 0, 0, precision, s,
-                            want_stats ? stats_of(o.out) : nullptr, &done));
-        stats_ok[o.out] = done;
+                            st_out, &done));
+        stats_ok[o.out] = done && st_out != nullptr;
     }
     BufView last = view(L, act_arena, p->out_buf);
     return mopa_scn_OutputLayer_updateOutput(m, last.ptr, last.ld, p->bufs[p->out_buf].channels, out, ld_out, s);

@@ -98,6 +98,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same with a per-output-row write mask: bit r of {m0..m3} set = row r of D (TMEM lane r) is NOT updated (PTX
+// "disable-output-lane"); always accumulates. The masks travel in four consecutive uniform registers (4 R2UR per call site).
+__device__ __forceinline__ void umma_tf32_masked(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%4, %5, %6, %7}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+        : "memory");
+}
+// zero 16 consecutive fp32 columns of this thread's TMEM lane (SASS: STTM); complete after tmem_st_wait()
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive on an mbarrier once every tcgen05 operation issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -163,6 +180,11 @@ __device__ __forceinline__ void cp_async16_zfill_pred_s(uint32_t dst, const void
         "{\n\t.reg .pred pg, pz;\n\tsetp.ne.b32 pg, %2, 0;\n\tsetp.ne.b32 pz, %3, 0;\n\t"
         "@pg cp.async.cg.shared.global [%0], [%1], 16, pz;\n\t}" ::"r"(dst),
         "l"(gmem_src), "r"(guard), "r"(zero));
+}
+// guarded plain copy: @guard dst[0..16) = src[0..16). One @P LDGSTS.
+__device__ __forceinline__ void cp_async16_guard_s(uint32_t dst, const void *gmem_src, uint32_t guard) {
+    asm volatile("{\n\t.reg .pred pg;\n\tsetp.ne.b32 pg, %2, 0;\n\t@pg cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst),
+                 "l"(gmem_src), "r"(guard));
 }
 // unguarded copy with the ignore-src operand: dst[0..16) = zero ? 0 : src[0..16)
 __device__ __forceinline__ void cp_async16_zfill_s(uint32_t dst, const void *gmem_src, uint32_t zero) {

@@ -96,6 +96,8 @@ class CompiledProgram:
             raise _Unsupported("table fed to a non-table module")
         level = self.bufs[b][0]
         if isinstance(mod, M.BatchNormalization):
+            if mod.nPlanes > 256:
+                raise _Unsupported("BatchNormalization over more than 256 planes")
             self._channels(b, mod.nPlanes)
             out = self._new_buf(level, mod.nPlanes)
             self._op(OP_BN, b, out, level, level, mod.nPlanes, mod.nPlanes, mod.leakiness, mod.eps, mod.momentum)
@@ -193,7 +195,7 @@ class _ProgramFunction(Function):
         if feats.shape[0] < n:
             raise _lib.ScnError("fewer feature rows than coordinates")
         prec = F._cfg["precision"]
-        stream = F._stream()
+        stream = F._stream(dev)
         n_active = (ctypes.c_int64 * prog.n_levels)()
         sizes = (ctypes.c_uint64 * 3)()
         with torch.cuda.device(dev):
@@ -210,7 +212,13 @@ class _ProgramFunction(Function):
         ctx.prog, ctx.meta, ctx.act, ctx.train, ctx.prec = prog, meta, act, train, prec
         ctx.sizes = (int(sizes[1]), int(sizes[2]))
         ctx.n_rows = feats.shape[0]
-        ctx.tensors = tensors  # the exact tensors the forward used (EMA swaps replace .data, not the tensor objects)
+        # The tensors the backward pass reads (conv weights for d_input, BatchNorm weight / bias) go through
+        # save_for_backward: an in-place update between this forward and its backward (optimizer.step(), .add_()) raises
+        # autograd's version-counter error instead of silently differentiating against the new values, exactly as for
+        # torch.nn layers. (torch_ema's .data.copy_ swaps bypass version counters for every layer, torch's included.)
+        ctx.read_idx = [i for i, (m, a) in enumerate(prog.slots) if not a.startswith("running_")]
+        ctx.save_for_backward(*[tensors[i] for i in ctx.read_idx])
+        ctx.n_slots = len(tensors)
         ctx.last_metadata = meta
         return out
 
@@ -219,9 +227,12 @@ class _ProgramFunction(Function):
         prog, meta, L = ctx.prog, ctx.meta, ctx.prog._lib
         d_out, ld_dout = F._rows(d_out)
         dev = d_out.device
-        tensors = ctx.tensors
+        saved = ctx.saved_tensors  # raises if one of them was modified in place since the forward
+        tensors = [None] * ctx.n_slots  # running statistics are not read by the backward pass
+        for i, t in zip(ctx.read_idx, saved):
+            tensors[i] = t
         need = ctx.needs_input_grad  # (prog, coords, train, feats, *trainable)
-        trainable_idx = [i for i, (m, a) in enumerate(prog.slots) if not a.startswith("running_")]
+        trainable_idx = ctx.read_idx
         sizes = [tensors[i].numel() for i in trainable_idx]
         with torch.cuda.device(dev):
             flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
@@ -234,7 +245,7 @@ class _ProgramFunction(Function):
                 else:
                     grads.append(None)
                 off += sz
-            params = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+            params = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() if t is not None else None for t in tensors])
             pgrads = (ctypes.c_void_p * len(tensors))(*ptrs)
             grad_arena = torch.empty(ctx.sizes[0], dtype=torch.uint8, device=dev)
             scratch = torch.empty(ctx.sizes[1], dtype=torch.uint8, device=dev)
@@ -242,7 +253,7 @@ class _ProgramFunction(Function):
             _lib.check(L.mopa_scn_Program_backward(
                 prog.handle, meta._h, params, pgrads, 1 if ctx.train else 0, ctx.prec, ctx.act.data_ptr(),
                 grad_arena.data_ptr(), scratch.data_ptr(), d_out.data_ptr(), ld_dout,
-                d_feats.data_ptr() if d_feats is not None else None, prog.in_planes, F._stream()))
+                d_feats.data_ptr() if d_feats is not None else None, prog.in_planes, F._stream(dev)))
         return (None, None, None, d_feats) + tuple(grads)
 
 

@@ -5,26 +5,59 @@ batchNormalization}.py: each Function's forward/backward is one or two calls int
 stream. No CPU fallback: a non-CUDA feature tensor raises.
 """
 import ctypes
+import os
 
 import torch
 from torch.autograd import Function
 
 from .. import _lib
 
-_cfg = {"precision": _lib.PREC_TF32}
+_PRECISIONS = {"tf32": _lib.PREC_TF32, "fp32": _lib.PREC_FP32}
+
+
+def _default_precision():
+    """fp32 products by default, as upstream SparseConvNet's SIMT kernels compute (a drop-in must not change the training
+    numerics silently). TF32 tensor-core products (the fast path: tcgen05 kernels, ~2^-11 relative error per product) are
+    opt-in: scn.set_precision('tf32') or MOPA_SCN_PRECISION=tf32, like torch.backends.cuda.matmul.allow_tf32."""
+    name = os.environ.get("MOPA_SCN_PRECISION", "fp32").lower()
+    if name not in _PRECISIONS:
+        raise _lib.ScnError("MOPA_SCN_PRECISION must be 'fp32' or 'tf32' (got %r)" % name)
+    return _PRECISIONS[name]
+
+
+_cfg = {"precision": _default_precision()}
 
 
 def set_precision(name):
-    """'tf32' (default: one TF32 MMA per product) or 'fp32' (3xTF32 split operands: fp32-equivalent, ~3x the MMA work)."""
-    _cfg["precision"] = {"tf32": _lib.PREC_TF32, "fp32": _lib.PREC_FP32}[name]
+    """'fp32' (default: 3xTF32 split operands, fp32-equivalent products) or 'tf32' (one TF32 MMA per product on the
+    tcgen05 kernels: the fast path, opt-in)."""
+    _cfg["precision"] = _PRECISIONS[name]
 
 
 def get_precision():
     return "tf32" if _cfg["precision"] == _lib.PREC_TF32 else "fp32"
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None):
+    """Raw handle of torch's current stream ON THE TENSOR'S DEVICE (not on the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _on_device(fn):
+    """Runs an autograd Function's forward / backward with the device of its first CUDA tensor argument current, so
+    that allocations, the stream handle (_stream()) and the library's cudaSetDevice all agree, and the caller's current
+    device is restored afterwards (the C entry points call cudaSetDevice(handle device) and do not restore it)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args):
+        for a in args:
+            if torch.is_tensor(a) and a.is_cuda:
+                with torch.cuda.device(a.device):
+                    return fn(*args)
+        return fn(*args)
+
+    return wrapped
 
 
 def _require_cuda(t, what):
@@ -83,14 +116,16 @@ class Metadata:
 
     def prepare_submanifold(self, spatial_size, filter_size=3):
         out = ctypes.c_int64(0)
-        _lib.check(self._lib.mopa_scn_Metadata_prepareSubmanifold(self._h, int(spatial_size), filter_size, _stream(),
-                                                                  ctypes.byref(out)))
+        with torch.cuda.device(self.device_index):
+            _lib.check(self._lib.mopa_scn_Metadata_prepareSubmanifold(self._h, int(spatial_size), filter_size, _stream(),
+                                                                      ctypes.byref(out)))
         return out.value
 
     def prepare_convolution(self, in_size, out_size, filter_size=2, stride=2):
         out = ctypes.c_int64(0)
-        _lib.check(self._lib.mopa_scn_Metadata_prepareConvolution(self._h, int(in_size), int(out_size), filter_size,
-                                                                  stride, _stream(), ctypes.byref(out)))
+        with torch.cuda.device(self.device_index):
+            _lib.check(self._lib.mopa_scn_Metadata_prepareConvolution(self._h, int(in_size), int(out_size), filter_size,
+                                                                      stride, _stream(), ctypes.byref(out)))
         return out.value
 
     def n_active(self, spatial_size):
@@ -137,6 +172,22 @@ class Metadata:
         return self._rulebook(self._lib.mopa_scn_Metadata_getConvolutionRuleBook, in_spatial_size, 8)
 
 
+    def tile_rulebook(self, spatial_size, kind):
+        """(lists int32 (tiles, K, 128), masks int32 (tiles, K, 4)) of the tile rulebook the tcgen05 conv kernels read;
+        kind: 'subm' (K = 27), 'child' (Convolution spatial_size -> /2 by coarse rows), 'select' (by fine rows)."""
+        code = {"subm": 0, "child": 1, "select": 2}[kind]
+        k = 27 if code == 0 else 8
+        tiles = ctypes.c_int64(0)
+        with torch.cuda.device(self.device_index):
+            _lib.check(self._lib.mopa_scn_Metadata_getTileRuleBook(self._h, int(spatial_size), code, ctypes.byref(tiles),
+                                                                   None, None))
+            lists = torch.empty(tiles.value, k, 128, dtype=torch.int32)
+            masks = torch.empty(tiles.value, k, 4, dtype=torch.int32)
+            _lib.check(self._lib.mopa_scn_Metadata_getTileRuleBook(self._h, int(spatial_size), code, ctypes.byref(tiles),
+                                                                   lists.data_ptr(), masks.data_ptr()))
+        return lists, masks
+
+
 # ---------------------------------------------------------------------------------------------------------------
 _bn_ws = {}
 
@@ -176,6 +227,7 @@ def _ptr(t):
 
 class InputLayerFunction(Function):
     @staticmethod
+    @_on_device
     def forward(ctx, feats, metadata, n_active):
         _require_cuda(feats, "InputLayer features")
         feats, ld = _rows(feats)
@@ -187,6 +239,7 @@ class InputLayerFunction(Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, d_out):
         m = ctx.meta
         d_out, ld = _rows(d_out)
@@ -199,6 +252,7 @@ class InputLayerFunction(Function):
 
 class OutputLayerFunction(Function):
     @staticmethod
+    @_on_device
     def forward(ctx, feats, metadata):
         _require_cuda(feats, "OutputLayer features")
         feats, ld = _rows(feats)
@@ -211,6 +265,7 @@ class OutputLayerFunction(Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, d_out):
         m = ctx.meta
         d_out, ld = _rows(d_out)
@@ -225,6 +280,7 @@ class _ConvFunction(Function):
     """kind: 'subm' (sizes = (spatial,)), 'conv' (in, out), 'deconv' (in = coarse, out = fine)."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, feats, weight, metadata, kind, sizes, n_out_rows, filter_size, stride):
         _require_cuda(feats, "convolution features")
         feats, ld_in = _rows(feats)
@@ -255,6 +311,7 @@ class _ConvFunction(Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, d_out):
         feats, w = ctx.saved_tensors
         m, kind, sizes = ctx.meta, ctx.kind, ctx.sizes
@@ -297,6 +354,7 @@ def sparse_conv(feats, weight, metadata, kind, sizes, n_out_rows, filter_size, s
 
 class BatchNormFunction(Function):
     @staticmethod
+    @_on_device
     def forward(ctx, feats, weight, bias, running_mean, running_var, eps, momentum, train, leakiness):
         _require_cuda(feats, "BatchNormalization features")
         feats, ld_in = _rows(feats)
@@ -315,6 +373,7 @@ class BatchNormFunction(Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, d_out):
         feats, weight, bias, save_mean, save_invstd = ctx.saved_tensors
         train, leakiness = ctx.cfg

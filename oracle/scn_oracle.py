@@ -358,3 +358,85 @@ def make_unet_state(in_channels=1, m=16, num_planes=7, seed=0, dtype=torch.float
     u(0, "2")
     bn("3", m)
     return st
+
+
+# ----------------------------------------------------------------------------------------------------------
+# UNetSCN_ED: the reference's unrolled encoder / decoder variant (mopa/models/scn_unet.py:38-134, VGG blocks,
+# residual_blocks=False, the configuration its own smoke test :222-239 builds with in_channels=3)
+# ----------------------------------------------------------------------------------------------------------
+_BN_KEYS = ("weight", "bias", "running_mean", "running_var")
+
+
+def make_ed_state(in_channels=3, m=16, seed=0, dtype=torch.float32):
+    """Random-init parameters under UNetSCN_ED's attribute names (`main_block2.1.0.weight`, `deconv6.3.weight`, ...)."""
+    g = torch.Generator().manual_seed(seed)
+    st = {}
+
+    def conv(name, vol, nin, nout):
+        st[name + ".weight"] = (torch.randn(vol, 1, nin, nout, generator=g, dtype=torch.float64) * (2.0 / nin / vol) ** 0.5).to(dtype)
+
+    def bn(name, c):
+        st[name + ".weight"] = (1.0 + 0.1 * torch.randn(c, generator=g, dtype=torch.float64)).to(dtype)
+        st[name + ".bias"] = (0.1 * torch.randn(c, generator=g, dtype=torch.float64)).to(dtype)
+        st[name + ".running_mean"] = torch.zeros(c, dtype=dtype)
+        st[name + ".running_var"] = torch.ones(c, dtype=dtype)
+
+    conv("down_in", 27, in_channels, m)
+    bn("main_block1.0", m)
+    conv("main_block1.1", 27, m, m)
+    for l in range(2, 8):  # scn_unet.py:197-207: BN(nPlanes), Sequential(Convolution k2 s2, BN(n), Submanifold n -> n)
+        a, b = (l - 1) * m, l * m
+        bn("main_block%d.0" % l, a)
+        conv("main_block%d.1.0" % l, 8, a, b)
+        bn("main_block%d.1.1" % l, b)
+        conv("main_block%d.1.2" % l, 27, b, b)
+    bn("deconv7.0", 7 * m)
+    conv("deconv7.1", 8, 7 * m, 6 * m)
+    for l in range(6, 1, -1):  # decoder(2 l m, (l - 1) m), scn_unet.py:136-144
+        a, b = 2 * l * m, (l - 1) * m
+        bn("deconv%d.0" % l, a)
+        conv("deconv%d.1" % l, 27, a, a // 2)
+        bn("deconv%d.2" % l, a // 2)
+        conv("deconv%d.3" % l, 8, a // 2, b)
+    bn("deconv1.0", 2 * m)
+    conv("deconv1.1", 27, 2 * m, m)
+    bn("output.0", m)
+    return st
+
+
+class OracleUNetSCN_ED:
+    """Functional restatement of UNetSCN_ED.forward (scn_unet.py:97-133) from the oracle's layer primitives."""
+
+    def __init__(self, state, m=16, full_scale=4096, dtype=torch.float64):
+        self.m, self.full_scale, self.dtype = m, full_scale, dtype
+        self.params = {k: v.detach().clone().to(dtype) for k, v in state.items()}
+        for k, v in self.params.items():
+            if "running_" not in k:
+                v.requires_grad_(True)
+
+    def _bn(self, x, name, train):
+        p = self.params
+        return batchnorm_leakyrelu(x, p[name + ".weight"], p[name + ".bias"], p[name + ".running_mean"],
+                                   p[name + ".running_var"], train)
+
+    def forward(self, coords, feats, train=True):
+        p = self.params
+        geo = self.geo = Geometry(coords, self.full_scale)
+        x = input_layer_forward(geo, torch.as_tensor(feats).to(self.dtype))
+        x = submanifold_conv(geo, 0, x, p["down_in.weight"])
+        feat = [None] * 8
+        feat[1] = submanifold_conv(geo, 0, self._bn(x, "main_block1.0", train), p["main_block1.1.weight"])
+        for l in range(2, 8):  # feature_l lives on level l - 1
+            y = self._bn(feat[l - 1], "main_block%d.0" % l, train)
+            y = strided_conv(geo, l - 2, y, p["main_block%d.1.0.weight" % l])
+            y = self._bn(y, "main_block%d.1.1" % l, train)
+            feat[l] = submanifold_conv(geo, l - 1, y, p["main_block%d.1.2.weight" % l])
+        d = strided_deconv(geo, 5, self._bn(feat[7], "deconv7.0", train), p["deconv7.1.weight"])
+        d = torch.cat([feat[6], d], 1)
+        for l in range(6, 1, -1):  # d: joined planes on level l - 1
+            y = submanifold_conv(geo, l - 1, self._bn(d, "deconv%d.0" % l, train), p["deconv%d.1.weight" % l])
+            y = strided_deconv(geo, l - 2, self._bn(y, "deconv%d.2" % l, train), p["deconv%d.3.weight" % l])
+            d = torch.cat([feat[l - 1], y], 1)
+        d = submanifold_conv(geo, 0, self._bn(d, "deconv1.0", train), p["deconv1.1.weight"])
+        d = self._bn(d, "output.0", train)
+        return output_layer_forward(geo, d)

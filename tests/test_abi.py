@@ -70,7 +70,7 @@ def test_library_builds_loads_and_exports_every_symbol():
     for name in _declarations():
         assert hasattr(lib, name), "libmopa_scn.so does not export %s" % name
     lib.mopa_scn_abi_version.restype = ctypes.c_int
-    assert lib.mopa_scn_abi_version() == 1
+    assert lib.mopa_scn_abi_version() == _lib.ABI_VERSION
 
 
 def test_metadata_new_fails_loudly_without_gpu():

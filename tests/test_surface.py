@@ -97,3 +97,59 @@ def test_cpu_tensors_fail_loudly():
     from mopa_b200._lib import ScnError
     with pytest.raises(ScnError):
         scn.InputLayer(3, 4096, mode=4)([torch.zeros(4, 4, dtype=torch.long), torch.ones(4, 1)])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reference's OWN model files through the shim (the drop-in boundary claim). /root/reference exists in
+# the build container only (never on the GPU box), so these run on CPU: they prove that mopa/models/scn_unet.py imports and
+# constructs unchanged on `import sparseconvnet as scn`, and that the module trees the GPU tests exercise
+# (mopa_b200/unet_scn.py, tests/ed_mirror.py) are identical to the reference's: same state_dict keys, shapes, module types
+# in traversal order, and the same compiled op list. The numerics of those trees are then checked on the GPU
+# (tests/test_gpu_parity.py, tests/test_gpu_reference_models.py).
+# ---------------------------------------------------------------------------------------------------------------
+REFERENCE = "/root/reference"
+
+
+def _reference_scn_unet():
+    import importlib
+    import os
+    import sys
+    if not os.path.isdir(os.path.join(REFERENCE, "mopa", "models")):
+        pytest.skip("the reference checkout is not present on this box")
+    if REFERENCE not in sys.path:
+        sys.path.insert(0, REFERENCE)
+    return importlib.import_module("mopa.models.scn_unet")  # its `import sparseconvnet as scn` resolves to the shim
+
+
+def _tree(net):
+    return ([(k, tuple(v.shape)) for k, v in net.state_dict().items()], [type(m).__name__ for m in net.modules()])
+
+
+def test_reference_unet_scn_builds_through_the_shim_and_equals_the_mirror():
+    ref = _reference_scn_unet()
+    from mopa_b200.unet_scn import UNetSCN
+    from mopa_b200.scn import compiler
+    theirs, ours = ref.UNetSCN(1), UNetSCN(1)  # xmuda.py:217-224 defaults
+    assert _tree(theirs) == _tree(ours)
+    pa, pb = compiler.CompiledProgram(theirs.sparseModel), compiler.CompiledProgram(ours.sparseModel)
+    assert pa.ops == pb.ops and pa.bufs == pb.bufs and pa.n_levels == pb.n_levels == 7
+    assert len(pa.ops) == 52  # 26 convolutions + 26 BatchNorms in one native program
+    ours.load_state_dict(theirs.state_dict(), strict=True)
+
+
+def test_ed_mirror_matches_the_reference_module_tree():
+    ref = _reference_scn_unet()
+    from tests.ed_mirror import UNetSCN_ED
+    theirs, ours = ref.UNetSCN_ED(3), UNetSCN_ED(3)  # in_channels = 3 as in the reference's own smoke test (:232)
+    ka, ma = _tree(theirs)
+    kb, mb = _tree(ours)
+    assert sorted(ka) == sorted(kb) and ma == mb
+    ours.load_state_dict(theirs.state_dict(), strict=True)
+
+
+def test_oracle_ed_state_uses_the_reference_key_layout():
+    from oracle import scn_oracle as so
+    from tests.ed_mirror import UNetSCN_ED
+    st = so.make_ed_state(3)
+    net = UNetSCN_ED(3)
+    assert {k: tuple(v.shape) for k, v in st.items()} == {k: tuple(v.shape) for k, v in net.state_dict().items()}
