@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libmopa_scn.so")
-SOURCES = ["geometry.cu", "conv.cu", "conv_tc.cu", "conv_dw_tc.cu", "bn_io.cu", "program.cu"]
+SOURCES = ["geometry.cu", "conv.cu", "conv_tc.cu", "conv_dw_tc.cu", "bn_io.cu", "program.cu", "xm_ops.cu", "vgi.cu"]
 HEADERS = ["common.cuh", "geometry.cuh", "ptx.cuh"]
 
 
@@ -24,7 +24,7 @@ def stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(INCLUDE, "mopa_scn.h")]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(INCLUDE, h) for h in ("mopa_scn.h", "mopa_xm.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

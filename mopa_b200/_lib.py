@@ -61,6 +61,19 @@ PROTOTYPES = {
     "mopa_scn_Program_forward": (_int, [_p, _p, _p, _i64, _p, _int, _int, _p, _p, _p, _i64, _p]),
     "mopa_scn_Program_backward": (_int, [_p, _p, _p, _p, _int, _int, _p, _p, _p, _p, _i64, _p, _i64, _p]),
     "mopa_scn_kernelLaunchCount": (_i64, []),
+    # include/mopa_xm.h
+    "mopa_xm_checkAsyncError": (_int, [_p]),
+    "mopa_xm_PixelGatherHeads_updateOutput": (_int, [_p, _int, _int, _int, _int, _p, _p, _i64, _p, _p, _p, _p, _int, _p, _p, _p, _p]),
+    "mopa_xm_pixelGatherWorkspaceBytes": (_sz, [_int, _int]),
+    "mopa_xm_PixelGatherHeads_backward": (_int, [_p, _p, _p, _int, _int, _int, _int, _i64, _p, _p, _int, _p, _p, _p, _p, _p, _p, _p,
+                                                 _p, _p, _sz, _p]),
+    "mopa_xm_KLDivLoss_updateOutput": (_int, [_p, _p, _i64, _int, _p, _p, _f, _p]),
+    "mopa_xm_maskConsStatsBytes": (_sz, [_int, _int, _int]),
+    "mopa_xm_MaskConsLoss_updateOutput": (_int, [_p, _p, _int, _i64, _int, _int, _int, _f, _p, _p, _p]),
+    "mopa_xm_MaskConsLoss_backward": (_int, [_p, _p, _int, _i64, _int, _int, _int, _f, _p, _f, _p, _p]),
+    "mopa_xm_vgiWorkspaceBytes": (_sz, [_i64, _int, _int]),
+    "mopa_xm_VgiPostProcess": (_int, [_p, _p, _i64, _int, _c.c_double, _c.c_double, _int, _int, _p, _p, _c.c_double, _i64, _int,
+                                      _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mopa_scn_Profile_enable": (_int, [_int]),
     "mopa_scn_Profile_count": (_i64, []),
     "mopa_scn_Profile_read": (_int, [_p, _i64]),

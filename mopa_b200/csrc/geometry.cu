@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(1024) k_scan_add(int32_t *__restrict__ out, in
 }
 
 // exclusive scan of int32; `bsum` scratch of ceil(n/1024) ints; total (device) may be null
-static int exclusive_scan(const int32_t *in, int32_t *out, int64_t n, int32_t *bsum, int32_t *total, cudaStream_t s) {
+int exclusive_scan(const int32_t *in, int32_t *out, int64_t n, int32_t *bsum, int32_t *total, cudaStream_t s) {
     if (n <= 0) {
         if (total) MOPA_CUDA(cudaMemsetAsync(total, 0, 4, s));
         return 0;

@@ -9,17 +9,17 @@ import pytest
 from mopa_b200 import _build, _lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HEADER = os.path.join(ROOT, "include", "mopa_scn.h")
+HEADERS = [os.path.join(ROOT, "include", h) for h in ("mopa_scn.h", "mopa_xm.h")]
 
 
 def _declarations():
     """name -> list of parameter strings, parsed from the header (comments stripped)."""
-    src = open(HEADER).read()
+    src = "\n".join(open(h).read() for h in HEADERS)
     src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
     src = re.sub(r"//[^\n]*", " ", src)
     src = re.sub(r"^\s*#.*$", " ", src, flags=re.M)
     decls = {}
-    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(mopa_scn_\w+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(mopa_(?:scn|xm)_\w+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
         name, args = m.group(2), " ".join(m.group(3).split())
         params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
         decls[name] = (" ".join(m.group(1).split()), params)
@@ -31,10 +31,10 @@ def _ctype_of(param):
     if "*" in p:
         return "ptr"
     base = p.rsplit(" ", 1)[0].strip() if " " in p else p
-    return {"int": "int", "int64_t": "i64", "float": "float", "size_t": "size", "uint64_t": "u64"}[base]
+    return {"int": "int", "int64_t": "i64", "float": "float", "double": "double", "size_t": "size", "uint64_t": "u64"}[base]
 
 
-_CT = {ctypes.c_int: "int", ctypes.c_int64: "i64", ctypes.c_float: "float", ctypes.c_size_t: "size",
+_CT = {ctypes.c_int: "int", ctypes.c_int64: "i64", ctypes.c_float: "float", ctypes.c_double: "double", ctypes.c_size_t: "size",
        ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr"}
 
 
