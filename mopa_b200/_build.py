@@ -8,7 +8,7 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-LIB = os.path.join(HERE, "libmopa_scn.so")
+LIB = os.environ.get("MOPA_SCN_LIB") or os.path.join(HERE, "libmopa_scn.so")  # MOPA_SCN_LIB: a debug build (e.g. trace)
 SOURCES = ["geometry.cu", "conv.cu", "conv_tc.cu", "conv_dw_tc.cu", "bn_io.cu", "program.cu", "xm_ops.cu", "vgi.cu"]
 HEADERS = ["common.cuh", "geometry.cuh", "ptx.cuh"]
 
@@ -21,6 +21,8 @@ def _nvcc():
 
 
 def stale():
+    if os.environ.get("MOPA_SCN_LIB"):
+        return False  # an explicitly chosen library is used as it is
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)

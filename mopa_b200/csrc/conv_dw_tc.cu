@@ -39,6 +39,7 @@ constexpr int kDwTcSub = 512;    // granularity of an item's row range (a multip
 constexpr int kDwTcMaxTiles = 2048;  // rulebook tiles per item (prefix counts in shared memory); caps rows per item
 constexpr int kDwTcList = kDwTcMaxTiles / 2 + 4;  // 8-byte slots of the prefix block (kDwTcMaxTiles + 1 ints)
 constexpr int kDwTcMaxStages = 12;
+constexpr int kDwTcAhead = 3;  // stages between fetching a rule's list entry and copying its rows
 
 struct DwTcPlan {
     int centre;  // 13 for a submanifold table, -1 otherwise
@@ -248,17 +249,28 @@ __global__ void __launch_bounds__(kDwTcThreads)
             tile = j;
             return __ldg(tl_k + (((int64_t)j * K) << 7) + (g - (int)lds_u32(pre_a + 4 * j)));
         };
-        int g = rt, t_cur = 0, e_cur = 0;
-        if (g < n_rules) e_cur = locate(g, t_cur);
-        for (int sidx = 0; sidx < n_stage; ++sidx) {
-            int t_nxt = 0, e_nxt = 0;
-            if (g + kDwTcTile < n_rules) e_nxt = locate(g + kDwTcTile, t_nxt);  // next stage's entry is in flight during this one
-            const uint32_t in_row = (uint32_t)e_cur & ((1u << kTileRowShift) - 1u);
-            const uint32_t out_row = (uint32_t)((t0 + t_cur) << 7) + ((uint32_t)e_cur >> kTileRowShift);
-            emit(swap ? out_row : in_row, swap ? in_row : out_row, g < n_rules ? 0u : 1u, sidx == n_stage - 1 ? 1u : 0u);
-            g += kDwTcTile;
-            t_cur = t_nxt;
-            e_cur = e_nxt;
+        // entries are fetched kDwTcAhead stages before their stage is filled (register ring with static indices): a stage
+        // is shorter than an L2 / HBM round trip
+        int e_q[kDwTcAhead], t_q[kDwTcAhead];
+#pragma unroll
+        for (int u = 0; u < kDwTcAhead; ++u) {
+            e_q[u] = 0;
+            t_q[u] = 0;
+            if (rt + kDwTcTile * u < n_rules) e_q[u] = locate(rt + kDwTcTile * u, t_q[u]);
+        }
+        for (int s0 = 0; s0 < n_stage; s0 += kDwTcAhead) {
+#pragma unroll
+            for (int u = 0; u < kDwTcAhead; ++u) {
+                const int sidx = s0 + u;
+                if (sidx < n_stage) {  // uniform over the producers
+                    const int g = rt + kDwTcTile * sidx, e_cur = e_q[u], t_cur = t_q[u];
+                    const int g_ahead = g + kDwTcTile * kDwTcAhead;
+                    if (g_ahead < n_rules) e_q[u] = locate(g_ahead, t_q[u]);
+                    const uint32_t in_row = (uint32_t)e_cur & ((1u << kTileRowShift) - 1u);
+                    const uint32_t out_row = (uint32_t)((t0 + t_cur) << 7) + ((uint32_t)e_cur >> kTileRowShift);
+                    emit(swap ? out_row : in_row, swap ? in_row : out_row, g < n_rules ? 0u : 1u, sidx == n_stage - 1 ? 1u : 0u);
+                }
+            }
         }
 
         // ================================================================= epilogue: TMEM -> partial slice

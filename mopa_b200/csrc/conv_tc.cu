@@ -37,10 +37,11 @@
 namespace mopa {
 
 constexpr int kTcTM = 256;            // output rows per CTA (two M = 128 tiles)
-constexpr int kTcThreads = 11 * 32;  // 8 gather warps, weight producer, two MMA issuers
+constexpr int kTcMaxThreads = 17 * 32;  // 8 gather warps, weight producer, up to 8 MMA issuers (tiles x accumulator sets)
 constexpr int kTcChunk = 32;          // input channels per pipeline step (one 128-byte swizzle row)
 constexpr int kTcAStage = 128 * 128;  // bytes: 128 rows x 128 bytes
 constexpr int kTcMaxSA = 12, kTcMaxSB = 8;
+constexpr int kTcAhead = 3;           // a gather warp fetches its rule-list entries this many of its stage-steps ahead
 constexpr int kTcStatsLd = 256;      // BatchNorm statistics block of a buffer: [sum x | sum x^2], 256 doubles each
 
 __host__ __device__ inline int tc_tmem_cols(int nt, int tpc = 2) {  // power of two >= 32 holding tpc accumulators of nt columns
@@ -103,10 +104,12 @@ __host__ __device__ inline TcSmem tc_smem_layout(int nt, int sa, int sb, int na 
     return L;
 }
 
-template <int NA, int LPR>
-__global__ void __launch_bounds__(kTcThreads, NA == 2 ? 1 : 2)
+// WIDE = 1: up to 17 warps, one CTA per SM; WIDE = 0: up to 13 warps (two tiles x two issuers), two CTAs per SM
+template <int NA, int LPR, int WIDE>
+__global__ void __launch_bounds__(WIDE ? kTcMaxThreads : 13 * 32, WIDE ? 1 : 2)
     k_conv_tc(Gather gt, const float *__restrict__ in, int64_t ld_in, float *__restrict__ out, int64_t ld_out,
-              const float *__restrict__ packed, int c_in, int NT, int SA, int SB, int TPC, int GW, double *__restrict__ stats) {
+              const float *__restrict__ packed, int c_in, int NT, int SA, int SB, int TPC, int GW, int ACC,
+              double *__restrict__ stats) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const TcSmem L = tc_smem_layout(NT, SA, SB, NA);
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(kTcThreads, NA == 2 ? 1 : 2)
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(d_full + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2, 7, 0);
     const int K = gt.volume;                                // 8 or 27: one lane per offset below
     const int chw = kTcChunk * NA;                          // channels per step
     const int nchunk = (c_in + chw - 1) / chw;              // steps per offset
@@ -124,12 +128,12 @@ __global__ void __launch_bounds__(kTcThreads, NA == 2 ? 1 : 2)
     const uint32_t a_stage = (uint32_t)NA * kTcAStage, b_stage = (uint32_t)NA * NT * 128;
     const int64_t tile0 = (int64_t)blockIdx.x * TPC, row0 = tile0 * 128;
     const int n_mt = (TPC == 2 && gt.n_out - row0 > 128) ? 2 : 1;  // tiles of this CTA that hold rows
-    const uint32_t tmem_cols = (uint32_t)tc_tmem_cols(NT, TPC);
+    const uint32_t tmem_cols = (uint32_t)tc_tmem_cols(NT, TPC * ACC);  // accumulator (set ai, tile mt) at column (ai TPC + mt) NT
 
     if (tid == 0) {
-        for (int i = 0; i < SA; ++i) { mbar_init(a_full + i, 32); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < SA; ++i) { mbar_init(a_full + i, 32 * (4 / GW)); mbar_init(a_empty + i, 1); }
         for (int i = 0; i < SB; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, n_mt); }
-        mbar_init(d_full, n_mt);
+        mbar_init(d_full, n_mt * ACC);
         mbar_fence_init();
     }
     if (warp == 9) tmem_alloc(tmem_ptr, tmem_cols);
@@ -145,13 +149,16 @@ __global__ void __launch_bounds__(kTcThreads, NA == 2 ? 1 : 2)
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
     if (warp < 4 * n_mt) {  // zero the accumulators (every MMA accumulates under a row mask): warp = (tile, TMEM lane quarter)
-        const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * NT);
-        for (int q = 0; q < NT / 16; ++q) tmem_st16_zero(taddr + 16 * q);
+        for (int ai = 0; ai < ACC; ++ai) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((ai * TPC + (warp >> 2)) * NT);
+            for (int q = 0; q < NT / 16; ++q) tmem_st16_zero(taddr + 16 * q);
+        }
         tmem_st_wait();
     }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2, 7, 1);
 
     if (warp < 8) {
         // ================================================================= gather warps
@@ -166,39 +173,54 @@ __global__ void __launch_bounds__(kTcThreads, NA == 2 ? 1 : 2)
         const char *in_c = reinterpret_cast<const char *>(in) + 16 * cl;
         const uint32_t ldb = (uint32_t)ld_in * 4;  // row pitch in bytes (feature matrices are far below 4 GB)
         const uint32_t sA_a = smem_u32(sA), full0_a = smem_u32(a_full), empty0_a = smem_u32(a_empty);
-        // The tile's stage-steps g = 0, 1, ... (live offsets in order x chunks) use stages mt + TPC g round the ring. GW
-        // gather warps are active per tile and warp wq fills the stage-steps g = wq (mod GW). GW divides the stages per
-        // tile, so a stage is always filled by the SAME warp: its a_empty wait is never more than one phase ahead of the
-        // barrier (mbarrier waits only tell odd from even phases; warps taking turns on a stage could run two uses ahead
-        // and alias). The other 4 - GW warps of the tile only work in the epilogue.
-        uint32_t rest = (live && wq < GW) ? liveset : 0u;  // live offsets from the current stage-step's on
-        int ch = wq;                                        // chunk of the current stage-step
+        // The tile's stage-steps g = 0, 1, ... (live offsets in order x chunks) use stages mt + TPC g round the ring. The
+        // tile's four gather warps form GW groups of CW = 4 / GW warps: group gi fills the stage-steps g = gi (mod GW), and
+        // inside a group warp mi copies the passes j = mi (mod CW) of each of its stage-steps (a pass = 32 / LPR rows). GW
+        // divides the stages per tile, so a stage is always filled by the SAME warps: their a_empty waits are never more
+        // than one phase ahead of the barrier (mbarrier waits only tell odd from even phases; warps taking turns on a
+        // stage could run two uses ahead and alias). GW = 4: one warp per stage-step (sparse tiles, ~15 rules per step);
+        // GW = 1: all four warps share every stage-step (dense tiles: a step's copy time is what bounds the ring).
+        const int CW = 4 / GW, gi = wq % GW, mi = wq / GW;
+        uint32_t rest = live ? liveset : 0u;  // live offsets from the current stage-step's on
+        int ch = gi;                           // chunk of the current stage-step
         while (rest && ch >= nchunk) { ch -= nchunk; rest &= rest - 1; }
-        int st = mt + TPC * wq;
+        int st = mt + TPC * gi;
         uint32_t ph = 1;  // parity of the a_empty wait of the next stage to fill
         while (st >= SA) { st -= SA; ph ^= 1; }
-        // list entries of this warp's next stage-step, fetched one step ahead: [0, 32) always, [32, 64) when present
-        int e_next = 0, e_next1 = 0;
-        auto prefetch = [&](uint32_t todo) {
-            if (!todo) return;
-            const int kn = __ffs(todo) - 1;
-            const int32_t *src = tl_tile + (kn << 7) + lane;
-            e_next = __ldg(src);
-            if (__shfl_sync(0xffffffffu, cnt, kn) > 32) e_next1 = __ldg(src + 32);
+        // List entries are fetched kTcAhead of this warp's stage-steps before they are used (register ring with static
+        // indices; [0, 32) always, [32, 64) when the step has them): a stage-step is shorter than an L2 / HBM round trip,
+        // and the device timeline showed the warp stalling on this load when it ran only one step ahead.
+        auto advance = [&](uint32_t &r, int &c) {
+            c += GW;
+            while (r && c >= nchunk) { c -= nchunk; r &= r - 1; }
         };
-        prefetch(rest);
+        int en[kTcAhead], en1[kTcAhead];
+        uint32_t rest_p = rest;  // prefetch cursor
+        int ch_p = ch;
+        auto prefetch = [&](int &e, int &e1) {
+            if (!rest_p) return;
+            const int kn = __ffs(rest_p) - 1;
+            const int32_t *src = tl_tile + (kn << 7) + lane;
+            e = __ldg(src);
+            if (__shfl_sync(0xffffffffu, cnt, kn) > 32) e1 = __ldg(src + 32);
+            advance(rest_p, ch_p);
+        };
+#pragma unroll
+        for (int u = 0; u < kTcAhead; ++u) { en[u] = en1[u] = 0; prefetch(en[u], en1[u]); }
         int tstep = 0;  // trace builds only
         while (rest) {
+#pragma unroll
+          for (int u = 0; u < kTcAhead; ++u) {
+            if (!rest) break;  // warp-uniform
             const int k = __ffs(rest) - 1;
             const int n = __shfl_sync(0xffffffffu, cnt, k);  // rules of my tile at this offset (0: only the other tile has some)
-            const int e0 = e_next, e1 = e_next1;
+            const int e0 = en[u], e1 = en1[u];
+            prefetch(en[u], en1[u]);
             const int cho = ch * (chw * 4);                  // byte offset of this step's channels in a feature row
             const int left = c_in - ch * chw;
             const bool has0 = cl < min(kTcChunk, left) / 4;                                 // this lane's piece exists in atom 0
             const bool has1 = NA == 2 && cl < max(0, min(kTcChunk, left - kTcChunk)) / 4;  // ... in atom 1
-            ch += GW;
-            while (rest && ch >= nchunk) { ch -= nchunk; rest &= rest - 1; }
-            prefetch(rest);
+            advance(rest, ch);
             TC_STAMP(warp == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 0, tstep);
             mbar_wait_s(empty0_a + 8 * st, ph);
             TC_STAMP(warp == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 1, tstep);
@@ -214,40 +236,41 @@ __global__ void __launch_bounds__(kTcThreads, NA == 2 ? 1 : 2)
                 cp_async16_guard_s(dst, src, (ok && has0) ? 1u : 0u);
                 if (NA == 2) cp_async16_guard_s(dst + kTcAStage, src + 128, (ok && has1) ? 1u : 0u);
             };
-            auto copy_block = [&](int e, int nb) {  // nb >= 1, warp-uniform
-                copy_pass(e, nb, 0);
-                if (nb > RPP) {
-                    copy_pass(e, nb, 1);
-                    if (nb > 2 * RPP) {
-#pragma unroll
-                        for (int j = 2; j < LPR; ++j)
-                            if (j * RPP < nb) copy_pass(e, nb, j);
-                    }
-                }
+            auto copy_block = [&](int e, int nb) {  // nb >= 1, warp-uniform; this warp's passes of the block: mi, mi + CW, ...
+                for (int j = mi; j * RPP < nb; j += CW) copy_pass(e, nb, j);
             };
             if (n > 0) copy_block(e0, min(n, 32));
             if (n > 32) copy_block(e1, min(n - 32, 32));
             for (int base = 64; base < n; base += 32)  // dense tiles and the centre offset
                 copy_block(__ldg(tl_tile + (k << 7) + base + lane), min(n - base, 32));
-            // every lane: "my copies into this stage have landed" arrives asynchronously (32 arrivals complete it)
+            // every lane: "my copies into this stage have landed" arrives asynchronously (32 CW arrivals complete it)
             cp_async_mbar_arrive_noinc_s(full0_a + 8 * st);
             TC_STAMP(warp == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 2, tstep);
             ++tstep;
             st += TPC * GW;
             if (st >= SA) { st -= SA; ph ^= 1; }
+          }
         }
 
         // ================================================================= epilogue: TMEM -> HBM, one output row per thread
+        TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2, 7, 2);
         if (live) {
             const int64_t row = row0 + 128 * mt + 32 * wq + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(mt * NT);
             mbar_wait(d_full, 0);
             tc_fence_after_sync();
+            TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2, 7, 3);
             float *dst = out + row * ld_out;
             float *s_part = reinterpret_cast<float *>(sA) + (size_t)warp * 2 * NT;  // the stage ring is idle by now
             for (int q = 0; q < NT / 16; ++q) {
                 float v[16];
                 tmem_ld16(taddr + 16 * q, v);  // warp-collective: every lane takes part, also beyond n_out
+                for (int ai = 1; ai < ACC; ++ai) {  // the accumulator sets of the tile's other issuers, in order
+                    float u[16];
+                    tmem_ld16(taddr + (uint32_t)(ai * TPC * NT) + 16 * q, u);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] += u[e];
+                }
                 if (row < gt.n_out) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -306,57 +329,71 @@ __global__ void __launch_bounds__(kTcThreads, NA == 2 ? 1 : 2)
                 }
             }
         }
-    } else if (warp - 9 < n_mt) {
-        // ================================================================= MMA issuers: warp 9 -> tile 0, warp 10 -> tile 1
-        // The whole warp runs the (warp-uniform) loops and waits; one elected lane executes the tcgen05 instructions, so
-        // descriptors and masks live in uniform registers.
-        const int mt = warp - 9;
+    } else if (warp - 9 < TPC * ACC && (warp - 9) / ACC < n_mt) {
+        // ================================================================= MMA issuers: warp 9 + mt ACC + ai
+        // Issuing one stage-step (proxy fence, descriptors through the uniform datapath, 4 tcgen05.mma, 2 commits) is a
+        // ~800-cycle serial chain per warp (device timeline, profiles/r02_tc_timeline.txt) while the tensor pipe itself is
+        // nearly idle, so a tile has ACC issuer warps: issuer ai takes the stage-steps g = ai (mod ACC) and accumulates them
+        // in ITS OWN TMEM accumulator (no ordering between MMAs of different threads is needed); the epilogue adds the ACC
+        // partial accumulators. ACC divides the A stages per tile and the B stages, so a given stage is always consumed by
+        // the same issuer and its barrier waits never run two phases ahead.
+        // The whole warp runs the (warp-uniform) loops and waits; one elected lane executes the tcgen05 instructions.
+        const int mt = (warp - 9) / ACC, ai = (warp - 9) % ACC;
         const uint4 mk = mt ? mk1 : mk0;
         const uint32_t idesc = umma_idesc_tf32(NT);
         const uint64_t desc_hi = umma_desc_sw128(0);  // everything but the start address
-        const uint32_t d = tmem_base + (uint32_t)(mt * NT);
-        int st = mt, ph = 0, stb = 0, phb = 0, tstep = 0;
-        for (uint32_t rest = liveset; rest; rest &= rest - 1) {
+        const uint32_t d = tmem_base + (uint32_t)((ai * TPC + mt) * NT);
+        uint32_t rest = liveset;
+        int ch = ai;
+        while (rest && ch >= nchunk) { ch -= nchunk; rest &= rest - 1; }
+        int st = mt + TPC * ai, ph = 0, stb = ai, phb = 0, tstep = 0;
+        while (st >= SA) { st -= SA; ph ^= 1; }
+        while (stb >= SB) { stb -= SB; phb ^= 1; }
+        while (rest) {
             const int k = __ffs(rest) - 1;
             const uint32_t m0 = __shfl_sync(0xffffffffu, mk.x, k), m1 = __shfl_sync(0xffffffffu, mk.y, k),
                            m2 = __shfl_sync(0xffffffffu, mk.z, k), m3 = __shfl_sync(0xffffffffu, mk.w, k);
             const bool any = (m0 | m1 | m2 | m3) != 0;  // warp-uniform: does THIS tile have a rule at offset k
-            for (int ch = 0; ch < nchunk; ++ch) {
-                mbar_wait(b_full + stb, phb);
-                const int left = c_in - ch * chw;
-                const int nk0 = min(kTcChunk, left) / 8;                                   // MMAs (K = 8 each) from atom 0
-                const int nk1 = NA == 2 ? max(0, min(kTcChunk, left - kTcChunk)) / 8 : 0;  // ... and from atom 1
-                const uint64_t b_desc = desc_hi | (uint64_t)((smem_u32(sB + (size_t)stb * b_stage) & 0x3FFFFu) >> 4);
-                TC_STAMP(mt == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 4, tstep);
-                mbar_wait(a_full + st, ph);
-                TC_STAMP(mt == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 5, tstep);
-                fence_proxy_async_smem();  // the gather warps' cp.async writes (generic proxy) -> UMMA reads
-                tc_fence_after_sync();
-                const uint64_t a_desc = desc_hi | (uint64_t)((smem_u32(sA + (size_t)st * a_stage) & 0x3FFFFu) >> 4);
-                if (elect_one()) {
-                    if (any) {
-                        for (int j = 0; j < nk0; ++j)  // + 32 bytes of K per MMA = + 2 in the address field
-                            umma_tf32_masked(d, a_desc + 2 * j, b_desc + 2 * j, idesc, ~m0, ~m1, ~m2, ~m3);
-                        for (int j = 0; j < nk1; ++j)  // second atom: 16 KB further in A, NT x 128 bytes further in B
-                            umma_tf32_masked(d, a_desc + (kTcAStage >> 4) + 2 * j, b_desc + (uint64_t)((NT * 128) >> 4) + 2 * j,
-                                             idesc, ~m0, ~m1, ~m2, ~m3);
-                    }
-                    umma_commit(a_empty + st);
-                    umma_commit(b_empty + stb);  // n_mt arrivals (one per issuer) release the weight stage
+            const int left = c_in - ch * chw;
+            const int nk0 = min(kTcChunk, left) / 8;                                   // MMAs (K = 8 each) from atom 0
+            const int nk1 = NA == 2 ? max(0, min(kTcChunk, left - kTcChunk)) / 8 : 0;  // ... and from atom 1
+            ch += ACC;
+            while (rest && ch >= nchunk) { ch -= nchunk; rest &= rest - 1; }
+            mbar_wait(b_full + stb, phb);
+            const uint64_t b_desc = desc_hi | (uint64_t)((smem_u32(sB + (size_t)stb * b_stage) & 0x3FFFFu) >> 4);
+            TC_STAMP(warp == 9 && lane == 0 && blockIdx.x == gridDim.x / 2, 4, tstep);
+            mbar_wait(a_full + st, ph);
+            TC_STAMP(warp == 9 && lane == 0 && blockIdx.x == gridDim.x / 2, 5, tstep);
+            fence_proxy_async_smem();  // the gather warps' cp.async writes (generic proxy) -> UMMA reads
+            tc_fence_after_sync();
+            TC_STAMP(warp == 9 && lane == 0 && blockIdx.x == gridDim.x / 2, 3, tstep);
+            const uint64_t a_desc = desc_hi | (uint64_t)((smem_u32(sA + (size_t)st * a_stage) & 0x3FFFFu) >> 4);
+            if (elect_one()) {
+                if (any) {
+                    for (int j = 0; j < nk0; ++j)  // + 32 bytes of K per MMA = + 2 in the address field
+                        umma_tf32_masked(d, a_desc + 2 * j, b_desc + 2 * j, idesc, ~m0, ~m1, ~m2, ~m3);
+                    for (int j = 0; j < nk1; ++j)  // second atom: 16 KB further in A, NT x 128 bytes further in B
+                        umma_tf32_masked(d, a_desc + (kTcAStage >> 4) + 2 * j, b_desc + (uint64_t)((NT * 128) >> 4) + 2 * j,
+                                         idesc, ~m0, ~m1, ~m2, ~m3);
                 }
-                __syncwarp();
-                TC_STAMP(mt == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 6, tstep);
-                ++tstep;
-                st += TPC;
-                if (st >= SA) { st -= SA; ph ^= 1; }
-                if (++stb == SB) { stb = 0; phb ^= 1; }
+                umma_commit(a_empty + st);
+                umma_commit(b_empty + stb);  // n_mt arrivals (one per tile) release the weight stage
             }
+            __syncwarp();
+            TC_STAMP(warp == 9 && lane == 0 && blockIdx.x == gridDim.x / 2, 6, tstep);
+            ++tstep;
+            st += TPC * ACC;
+            if (st >= SA) { st -= SA; ph ^= 1; }
+            stb += ACC;
+            if (stb >= SB) { stb -= SB; phb ^= 1; }
         }
-        if (elect_one()) umma_commit(d_full);  // n_mt arrivals complete it
+        if (elect_one()) umma_commit(d_full);  // n_mt * ACC arrivals complete it
         __syncwarp();
     }
+    TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2, 7, 4);
     tc_fence_before_sync();
     __syncthreads();
+    TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2, 7, 5);
     if (warp == 9) tmem_dealloc(tmem_base, tmem_cols);
     if (stats && tid < 2 * NT) {  // [0, NT): sum x, [NT, 2 NT): sum x^2; warps of the tiles that hold rows, in order
         const float *s_all = reinterpret_cast<const float *>(sA);
@@ -404,57 +441,78 @@ int pack_weights_tc_batch(TcPackJobs &jobs, int n_jobs, cudaStream_t s) {
     return 0;
 }
 
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *packed,
                   int c_in, int c_out, double *stats, cudaStream_t s) {
     const int nt = c_out;
-    // ring depths. An A stage is 16 KB but carries only the few rows that have a rule at that offset, so the gather bytes
-    // in flight are set by the NUMBER of stages (kept even for two-tile CTAs: tile 0 uses the even stages, tile 1 the odd).
-    static const int want_ctas = [] { const char *e = getenv("MOPA_TC_CTAS"); return e ? atoi(e) : 2; }();
-    static const int want_sb = [] { const char *e = getenv("MOPA_TC_SB"); return e ? atoi(e) : 4; }();
-    static const int want_tpc = [] { const char *e = getenv("MOPA_TC_TPC"); return e ? atoi(e) : 0; }();
-    static const int want_sa = [] { const char *e = getenv("MOPA_TC_SA"); return e ? atoi(e) : 0; }();  // cap on the A stages
-    // one M tile per CTA only for levels so small that 256-row CTAs would leave SMs empty (the weight tiles are
-    // streamed per CTA: halving the rows per CTA doubles that traffic, which costs more than it gains on mid-size levels)
+    MOPA_CHECK(gt.tl && gt.tm, "conv_tc: the gather has no tile rulebook");
+    // Shape of the CTA (all overridable for sweeps: MOPA_TC_{CTAS,TPC,SA,SB,NA,ACC}):
+    //   tpc  tiles (128 output rows) per CTA: 2 on the large levels (the weight tiles are streamed per CTA), 1 where
+    //        256-row CTAs would leave SMs empty
+    //   na   32-channel atoms per stage-step: 2 on the small levels (half the steps where the per-step latency dominates)
+    //   acc  issuer warps / TMEM accumulator sets per tile (the issue chain of a stage-step is the serial bottleneck)
+    //   sa   A stages per CTA (sx = sa / tpc per tile), sb weight stages; acc and the gather warps per tile (gw) must
+    //        divide sx, acc must divide sb: every stage then always meets the same producer and consumer warp
+    static const int want_ctas = env_int("MOPA_TC_CTAS", 2), want_sb = env_int("MOPA_TC_SB", 4), want_tpc = env_int("MOPA_TC_TPC", 0);
+    static const int want_sa = env_int("MOPA_TC_SA", 0), want_na = env_int("MOPA_TC_NA", 0), want_acc = env_int("MOPA_TC_ACC", 2);
     const int sms = num_sms();
     const int tpc = want_tpc ? want_tpc : (ceil_div(gt.n_out, kTcTM) > sms ? 2 : 1);
-    int sb = want_sb < 2 ? 2 : (want_sb > kTcMaxSB ? kTcMaxSB : want_sb);
-    // two 32-channel atoms per step on the small levels (one CTA per SM, bound by the per-step latency)
-    static const int want_na = [] { const char *e = getenv("MOPA_TC_NA"); return e ? atoi(e) : 0; }();
     const int na = want_na ? want_na : ((tpc == 1 && c_in >= 64 && ceil_div(gt.n_out, 128) <= sms) ? 2 : 1);
-    while (sb > 2 && (size_t)sb * na * nt * 128 > (size_t)(tpc == 2 ? 64 : 32 * na) * 1024) --sb;
-    // two CTAs per SM when that helps: not when the whole grid fits one CTA per SM anyway (then the one CTA gets all stages)
-    bool two = want_ctas >= 2 && tc_tmem_cols(nt, tpc) <= 256 && (nt <= 64 || tpc == 1) &&
-               ceil_div(gt.n_out, 128 * tpc) > sms;
-    // (Three CTAs per SM with a 4-stage ring were measured on the narrow, large levels: within noise of two CTAs with six
-    // stages, and the 11-warp CTA does not fit three times in the register file without spills; not kept.)
-    int sa = 0;
+    bool two = want_ctas >= 2 && (nt <= 64 || tpc == 1) && ceil_div(gt.n_out, 128 * tpc) > sms;  // two CTAs per SM
+    int acc = 1, sb = 2, sa = 0;
     size_t cap = 0;
     for (;;) {
         cap = two ? (size_t)113 * 1024 : (size_t)226 * 1024;
-        sa = want_sa >= 2 && want_sa <= kTcMaxSA ? want_sa - want_sa % tpc : kTcMaxSA;
-        while (sa > 2 && (size_t)tc_smem_layout(nt, sa, sb, na).total + 1024 > cap) sa -= tpc;
-        if (!two || sa >= 4) break;
-        two = false;  // too few stages at two CTAs per SM: take the whole SM
+        acc = want_acc >= 4 ? 4 : (want_acc >= 2 ? 2 : 1);
+        while (acc > 1 && (tc_tmem_cols(nt, tpc * acc) > (two ? 256 : 512) || 32 * (9 + tpc * acc) > (two ? 13 * 32 : kTcMaxThreads))) acc >>= 1;
+        sb = want_sb >= 4 ? 4 : 2;
+        while (sb > 2 && (size_t)sb * na * nt * 128 > (size_t)(tpc == 2 ? 64 : 32 * na) * 1024) sb -= 2;
+        if (acc > sb) acc = sb;
+        const int unit = tpc * acc;  // sa must be a multiple of it
+        sa = want_sa >= unit && want_sa <= kTcMaxSA ? want_sa : kTcMaxSA;
+        sa -= sa % unit;
+        while (sa > unit && (size_t)tc_smem_layout(nt, sa, sb, na).total + 1024 > cap) sa -= unit;
+        const bool fits = (size_t)tc_smem_layout(nt, sa, sb, na).total + 1024 <= cap && tc_tmem_cols(nt, tpc * acc) <= (two ? 256 : 512);
+        if (fits && (!two || sa >= 2 * tpc)) break;
+        if (two) { two = false; continue; }  // too little room at two CTAs per SM: take the whole SM
+        MOPA_CHECK(fits, "conv_tc: shared memory / TMEM layout does not fit");
+        break;
     }
-    MOPA_CHECK((size_t)tc_smem_layout(nt, sa, sb, na).total + 1024 <= cap && sa >= 2, "conv_tc: shared memory layout does not fit");
     const size_t smem = (size_t)tc_smem_layout(nt, sa, sb, na).total + 1024;
-    MOPA_CHECK(gt.tl && gt.tm, "conv_tc: the gather has no tile rulebook");
     static std::atomic<uint64_t> configured{0};
     MOPA_TRY(once_per_device(configured, [] {
-        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<2, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<2, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         return 0;
     }));
-    const int sx = sa / tpc;  // stages per tile; the active gather warps per tile must divide it (see the kernel)
-    const int gw = sx % 4 == 0 ? 4 : (sx % 2 == 0 ? 2 : 1);
+    const int sx = sa / tpc;
+    static const int want_gw = env_int("MOPA_TC_GW", 2);  // gather groups per tile (1: all four warps share every stage-step)
+    int gw = want_gw >= 4 ? 4 : (want_gw >= 2 ? 2 : 1);
+    while (gw > 1 && sx % gw) gw >>= 1;
+    const unsigned threads = 32u * (unsigned)(9 + tpc * acc);
     dim3 grid((unsigned)ceil_div(gt.n_out, 128 * tpc));
-    if (na == 2)
-        k_conv_tc<2, 8><<<grid, kTcThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc, gw, stats);
-    else if (c_in == 16)
-        k_conv_tc<1, 4><<<grid, kTcThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc, gw, stats);
-    else
-        k_conv_tc<1, 8><<<grid, kTcThreads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc, gw, stats);
+    const bool wide = threads > 13 * 32;
+#define MOPA_TC_LAUNCH(NA_, LPR_)                                                                                         \
+    do {                                                                                                                  \
+        if (wide)                                                                                                         \
+            k_conv_tc<NA_, LPR_, 1><<<grid, threads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc, \
+                                                                gw, acc, stats);                                          \
+        else                                                                                                              \
+            k_conv_tc<NA_, LPR_, 0><<<grid, threads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc, \
+                                                                gw, acc, stats);                                          \
+    } while (0)
+    if (na == 2) MOPA_TC_LAUNCH(2, 8);
+    else if (c_in == 16) MOPA_TC_LAUNCH(1, 4);
+    else MOPA_TC_LAUNCH(1, 8);
+#undef MOPA_TC_LAUNCH
     MOPA_LAUNCHED();
     return 0;
 }

@@ -379,7 +379,10 @@ def test_compiled_path_handles_device_coords_surplus_rows_and_no_grad(scn):
 
 
 def test_unet_eval_mode_and_batch_separation(scn):
-    """Eval-mode BN has no cross-sample coupling: a scan's outputs are bit-identical alone or inside a batch."""
+    """Eval-mode BN has no cross-sample coupling: a scan's outputs are the same alone or inside a batch. Not bit for bit:
+    a scan's voxels sit at different offsets inside the 128-row tiles in the two runs, and the conv kernel deals a tile's
+    live filter offsets to two TMEM accumulator sets (conv_tc.cu, ACC), so the fp32 summation order of a row differs.
+    With MOPA_TC_ACC=1 the two runs are bit-identical (checked when that variable is set)."""
     from mopa_b200.unet_scn import UNetSCN
     scn.set_precision("tf32")
     coords, feats = small_batch(2, 200, 3)
@@ -388,7 +391,11 @@ def test_unet_eval_mode_and_batch_separation(scn):
         both = net([torch.from_numpy(coords), torch.from_numpy(feats).cuda()])
         sel = coords[:, 3] == 1
         alone = net([torch.from_numpy(coords[sel][:, :3].copy()), torch.from_numpy(feats[sel]).cuda()])
-    assert torch.equal(both[torch.from_numpy(sel).cuda()], alone)
+    import os
+    got = both[torch.from_numpy(sel).cuda()]
+    if os.environ.get("MOPA_TC_ACC") == "1":
+        assert torch.equal(got, alone)
+    assert rel_err(got, alone) < 2e-3  # tf32 products: reordered sums flip a few operand roundings downstream
 
 
 def test_unet_translation_by_64_is_bit_identical_and_duplicates_agree(scn):
