@@ -33,8 +33,8 @@ N_ROTATE = 4  # distinct batches cycled through the timed region
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sensor", default="nuscenes", choices=["nuscenes", "kitti"])
     ap.add_argument("--batch", type=int, default=8, help="scans per GPU")
@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode (3xTF32) ms/step leg")
     return ap.parse_args()
 
 
@@ -110,6 +111,7 @@ def cpu_oracle_step(net_state, coords, feats):
 
 
 def cpu_baseline(a, max_seconds=20.0):
+    use_all_host_threads()
     from mopa_b200 import synth
     from oracle import scn_oracle as so
     n_az = synth.azimuth_for_points(a.points, a.sensor) if a.points else None
@@ -128,10 +130,18 @@ def cpu_baseline(a, max_seconds=20.0):
             "host_cpus": os.cpu_count()}
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm runs on rank 0 alone and may use every core the box has."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     from mopa_b200 import synth
     from oracle import scn_oracle as so
     n_az = synth.azimuth_for_points(a.points, a.sensor) if a.points else None
@@ -210,16 +220,64 @@ def roofline_pass(net, batches_dev, steps, peaks):
     ach = b / t / 1e9 if t > 0 else 0.0
     traffic = None  # dram bytes per launch of the same launches, from one `ncu --set full` capture (profiles/README.md)
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_tc_traffic.json")))["dram_bytes_per_launch"]
+        for name in ("r02_conv_tc_traffic.json", "r01_conv_tc_traffic.json"):  # newest ncu capture that is committed
+            path = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(path):
+                traffic = json.load(open(path))["dram_bytes_per_launch"]
+                break
     except (OSError, ValueError, KeyError):
         pass
-    return {"bound": "hbm", "kernel": "k_conv_tc (tcgen05: cp.async gather -> TF32 UMMA -> TMEM accumulate; conv forward + d_input, %d launches/step)" % (n // max(steps, 1)),
+    return {"bound": "hbm", "bound_note": "roofline denominator = HBM copy peak as the task prescribes; the kernel itself is bound by the "
+            "latency of its per-stage hand-off chain (gather -> land -> MMA issue -> commit), not by HBM or L2 bytes: see "
+            "profiles/r02_tc_timeline.txt and DESIGN.md 4.1",
+            "kernel": "k_conv_tc (tcgen05: tile-rulebook cp.async gather -> masked TF32 UMMA -> TMEM accumulate; conv forward + d_input, %d launches/step)" % (n // max(steps, 1)),
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
             "launches_timed": n, "avg_launch_us": 1e6 * t / max(n, 1), "algorithmic_bytes_per_launch": b / max(n, 1),
             "tflops_useful": fl / t / 1e12 if t > 0 else 0.0,
             "per_class": {k: {"ms_per_step": 1e3 * v[1] / max(steps, 1), "gbs": v[0] / v[1] / 1e9 if v[1] else 0.0,
                               "frac": v[0] / v[1] / 1e9 / peak if v[1] else 0.0, "launches": v[2]} for k, v in cls.items()}}
+
+
+def geometry_pass(batches_dev, peaks, reps=10):
+    """Achieved HBM GB/s of the integer part of a forward (north_star: "achieved HBM GB/s for hashing"): voxel hashing +
+    first-occurrence ids + CSR lists, 6 strided levels, 7 neighbour tables and the tile rulebooks, timed with CUDA events
+    on the launching stream through the per-module entry points; algorithmic bytes per SURVEY.md 8(d):
+    voxelise N (32 + 4 + 4 Cin) + 4 V0 Cin; submanifold rulebook 16 V + 8 R per level; strided 16 Vl + 8 Vl + 16 Vl+1."""
+    import mopa_b200.scn as scn
+    from mopa_b200.scn import functional as F
+    ms, bytes_ = [], 0
+    for rep in range(reps + 2):
+        c, f = batches_dev[rep % len(batches_dev)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        m = F.Metadata(3, f.device)
+        v = [m.set_locations(c, 4096, 4)]
+        size = 4096
+        for level in range(7):
+            m.prepare_submanifold(size, 3)
+            if level < 6:
+                v.append(m.prepare_convolution(size, size // 2, 2, 2))
+                size //= 2
+        e1.record()
+        torch.cuda.synchronize()
+        if rep >= 2:
+            ms.append(e0.elapsed_time(e1))
+        if rep == reps + 1:  # rule counts through the inspection call, outside the timed region
+            n = c.shape[0]
+            bytes_ = n * (32 + 4 + 4) + 4 * v[0]
+            size = 4096
+            for level in range(7):
+                bytes_ += 16 * v[level] + 8 * sum(m.submanifold_rule_counts(size))
+                if level < 6:
+                    bytes_ += 16 * v[level] + 8 * v[level] + 16 * v[level + 1]
+                size //= 2
+        del m
+    peak = peaks.get("hbm_gbs", 6650.0)
+    med = float(np.median(ms))
+    return {"ms_per_forward": med, "algorithmic_bytes": int(bytes_), "achieved_gbs": bytes_ / med / 1e6,
+            "frac": bytes_ / med / 1e6 / peak, "note": "k_insert / k_flag_first / scans / k_subm_table / k_tile_lists ... incl. the "
+            "7 count read-backs (host syncs); in a step this runs on its own stream ahead of the convolutions"}
 
 
 def run_ours(a):
@@ -240,21 +298,32 @@ def run_ours(a):
     torch.manual_seed(0)
     net = UNetSCN(1).cuda()
     parallel.broadcast_parameters(net)
-    bucket = parallel.FlatGradBucket(net.parameters())
+    bucket = parallel.FlatGradBucket(net.parameters()).attach()  # the compiled backward writes grads into the bucket
 
     host = make_batches(a, rank, N_ROTATE)
     pinned = [(torch.from_numpy(c).pin_memory(), torch.from_numpy(f).pin_memory()) for c, f in host]
     dev = [(c.cuda(), f.cuda()) for c, f in pinned]
     pts_per_step = [c.shape[0] for c, _ in host]
+    ar_events = []  # (start, end) CUDA events around the gradient all-reduce of each timed step
 
-    def step_resident(i):
+    def all_reduce_timed(record):
+        if world == 1 or not record:
+            bucket.all_reduce()
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        bucket.all_reduce()
+        e1.record()
+        ar_events.append((e0, e1))
+
+    def step_resident(i, record=False):
         c, f = dev[i % N_ROTATE]
         bucket.zero()
         out = net([c, f])
         out.sum().backward()
-        bucket.all_reduce()
+        all_reduce_timed(record)
 
-    def step_e2e(i):
+    def step_e2e(i, record=False):
         c, f = pinned[i % N_ROTATE]
         bucket.zero()
         out = net([c, f.cuda(non_blocking=True)])  # coords go H2D inside InputLayer (host pointer, as the reference passes them)
@@ -268,42 +337,61 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn):
-        for i in range(a.warmup):
+    def timed(fn, steps, warmup, record=False):
+        """The contract's timed region: `warmup` untimed steps, barrier + synchronize, EXACTLY `steps` steps, barrier +
+        synchronize; device time from CUDA events on the launching stream, MAX over ranks. One extra event per step gives
+        the per-step distribution (median / p10 / p90) without changing what is timed."""
+        for i in range(warmup):
             fn(i)
         barrier()
         l0 = _lib.kernel_launches()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         t0 = time.time()
-        e0.record()
-        for i in range(a.steps):
-            fn(a.warmup + i)
-        e1.record()
+        ev[0].record()
+        for i in range(steps):
+            fn(warmup + i, record) if record else fn(warmup + i)
+            ev[i + 1].record()
         barrier()
         t1 = time.time()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        pts = torch.tensor([float(sum(pts_per_step[(a.warmup + i) % N_ROTATE] for i in range(a.steps)))], device="cuda")
+        total = ev[0].elapsed_time(ev[-1])
+        per = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)])
+        mine = torch.tensor([total, float(np.median(per)), float(np.percentile(per, 10)), float(np.percentile(per, 90)),
+                             float(sum(pts_per_step[(warmup + i) % N_ROTATE] for i in range(steps)))], device="cuda",
+                            dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            dist.all_reduce(pts, op=dist.ReduceOp.SUM)
-        return float(ms) * 1e-3, float(pts), _lib.kernel_launches() - l0, (t0, t1)
+            dist.all_gather(allr, mine)
+        else:
+            allr = [mine]
+        rows = [[float(x) for x in r] for r in allr]
+        return {"sec": max(r[0] for r in rows) * 1e-3, "pts": sum(r[4] for r in rows), "launches": _lib.kernel_launches() - l0,
+                "window": (t0, t1), "median_ms": max(r[1] for r in rows), "p10_ms": max(r[2] for r in rows),
+                "p90_ms": max(r[3] for r in rows),
+                "per_rank": [{"ms_per_step": r[0] / steps, "median_ms": r[1], "points_per_step": r[4] / steps} for r in rows]}
 
     sampler = ClockSampler(local) if rank == 0 else None
     time.sleep(0.3)
-    sec, pts, launches, win = timed(step_resident)
-    clocks = sampler.window(*win) if sampler else None
-    e_sec, e_pts, _, _ = timed(step_e2e)
+    res = timed(step_resident, a.steps, a.warmup, record=True)
+    clocks = sampler.window(*res["window"]) if sampler else None
+    ar_us = float(np.median([e0.elapsed_time(e1) for e0, e1 in ar_events])) * 1e3 if ar_events else 0.0
+    e2e = timed(step_e2e, a.steps, a.warmup)
     if sampler:
         sampler.stop()
+    fp32 = None
+    if not a.no_fp32 and a.precision != "fp32":  # the parity mode (3xTF32 products), same steps, fewer of them
+        scn.set_precision("fp32")
+        fp32 = timed(step_resident, max(5, min(20, a.steps // 5)), 3)
+        scn.set_precision(a.precision)
 
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except (OSError, ValueError):
         pass
-    roof = None
+    roof = geo = None
     if rank == 0 and not a.no_roofline:
         roof = roofline_pass(net, dev, min(a.steps, 8), peaks)
+        geo = geometry_pass(dev, peaks)
     if world > 1:
         dist.barrier()
     cpu = None
@@ -311,18 +399,27 @@ def run_ours(a):
         cpu = cpu_baseline(a)
     if rank == 0:
         h2d = int(np.mean([c.numel() * 8 + f.numel() * 4 for c, f in pinned]))
-        print(json.dumps({
-            "metric": METRIC, "value": pts / sec, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": 1e3 * sec / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        pr = res["per_rank"]
+        line = {
+            "metric": METRIC, "value": res["pts"] / res["sec"], "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * res["sec"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": a.precision if a.precision == "tf32" else "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "global_batch_scans": a.batch * world,
-                       "points_per_step": pts / a.steps, "parallelism": "dp%d (scan-sharded, 1 grad all-reduce/step)" % world,
+                       "points_per_step": res["pts"] / a.steps, "parallelism": "dp%d (scan-sharded, 1 grad all-reduce/step)" % world,
                        "l2": "%d distinct batches rotated; a step touches >1 GB of activations, far beyond the 126 MB L2" % N_ROTATE,
                        "storage": "fp32 features/grads, tf32 tensor-core products, fp32 accumulate" if a.precision == "tf32"
                                   else "fp32 storage, 3xTF32 split products (fp32-equivalent)"},
-            "e2e": {"value": e_pts / e_sec, "unit": UNIT, "ms_per_step": 1e3 * e_sec / a.steps,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}))
+            "step_ms": {"median": res["median_ms"], "p10": res["p10_ms"], "p90": res["p90_ms"],
+                        "note": "per-step CUDA-event times inside the same timed region; max over ranks"},
+            "e2e": {"value": e2e["pts"] / e2e["sec"], "unit": UNIT, "ms_per_step": 1e3 * e2e["sec"] / a.steps,
+                    "median_ms": e2e["median_ms"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "per_rank": pr,
+            "imbalance": {"points_max_over_min": max(r["points_per_step"] for r in pr) / max(1.0, min(r["points_per_step"] for r in pr)),
+                          "ms_max_over_min": max(r["ms_per_step"] for r in pr) / max(1e-9, min(r["ms_per_step"] for r in pr))},
+            "all_reduce_us_median": ar_us,
+            "fp32_ms_per_step": (1e3 * fp32["sec"] / max(5, min(20, a.steps // 5))) if fp32 else None,
+            "gpu_launches": res["launches"], "clocks": clocks, "roofline": roof, "geometry": geo, "cpu_baseline": cpu}
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -492,6 +492,19 @@ static bool bn_fused_enabled() {  // MOPA_SCN_NO_BNFUSED=1: the two-kernel path 
     const char *e = getenv("MOPA_SCN_NO_BNFUSED");
     return !(e && e[0] == '1');
 }
+// The cooperative single-kernel BatchNorm (statistics -> grid barrier -> apply) is only used from this many elements
+// (rows x planes) on; the default is "never". Measured in round 2 (profiles/r02_bn_paths.txt): a cooperative launch needs
+// its whole grid co-resident, so it cannot start while the d_weight kernels of the side stream occupy SMs, and nothing else
+// can start while it spins on its grid barrier: in the backward pass that serialises the two streams. Two plain kernels
+// per BatchNorm cost ~10 % more device time per op in isolation and make the whole step 0.15-0.25 ms faster.
+// MOPA_SCN_BN_FUSED_MIN=<elements> re-enables the cooperative kernel from that size on (A/B measurements, tests).
+static int64_t bn_fused_min_elems() {
+    static const int64_t v = [] {
+        const char *e = getenv("MOPA_SCN_BN_FUSED_MIN");
+        return e ? (int64_t)atoll(e) : (int64_t)1 << 62;
+    }();
+    return v;
+}
 template <int VEC, bool BWD>
 static int launch_bn_fused(const BnShapeArgs &A, cudaStream_t s) {
     const int tx = A.planes / VEC;
@@ -607,7 +620,7 @@ int bn_forward(const float *in, int64_t ld_in, float *out, int64_t ld_out, float
         prof_end(prof, s);
         return 0;
     }
-    if (train && sh.vec == 4 && bn_fused_enabled()) {
+    if (train && sh.vec == 4 && bn_fused_enabled() && n_active * planes >= bn_fused_min_elems()) {
         const BnShapeArgs A{in, ld_in, nullptr, 0, out, ld_out, n_active, planes, ws, nullptr, nullptr, weight, bias, leakiness,
                             1, eps, momentum, save_mean, save_invstd, running_mean, running_var, nullptr, nullptr, 0};
         const int rc = launch_bn_fused<4, false>(A, s);
@@ -656,7 +669,7 @@ int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, con
     MOPA_CHECK(sh.block.x * sh.block.y <= 256, "BatchNormalization: unaligned features with more than 256 planes");
     float *ws = reinterpret_cast<float *>(workspace);
     const int prof = prof_begin(50, nullptr, planes, planes, n_active, s);
-    if (sh.vec == 4 && bn_fused_enabled()) {
+    if (sh.vec == 4 && bn_fused_enabled() && n_active * planes >= bn_fused_min_elems()) {
         const BnShapeArgs A{in, ld_in, d_out, ld_dout, d_in, ld_din, n_active, planes, ws, save_mean, save_invstd, weight, bias,
                             leakiness, train, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, d_weight, d_bias, accumulate};
         const int rc = launch_bn_fused<4, true>(A, s);

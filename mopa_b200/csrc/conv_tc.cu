@@ -41,7 +41,7 @@ constexpr int kTcMaxThreads = 17 * 32;  // 8 gather warps, weight producer, up t
 constexpr int kTcChunk = 32;          // input channels per pipeline step (one 128-byte swizzle row)
 constexpr int kTcAStage = 128 * 128;  // bytes: 128 rows x 128 bytes
 constexpr int kTcMaxSA = 12, kTcMaxSB = 8;
-constexpr int kTcAhead = 3;           // a gather warp fetches its rule-list entries this many of its stage-steps ahead
+constexpr int kTcAhead = 1;           // a gather warp fetches its rule-list entries this many of its stage-steps ahead
 constexpr int kTcStatsLd = 256;      // BatchNorm statistics block of a buffer: [sum x | sum x^2], 256 doubles each
 
 __host__ __device__ inline int tc_tmem_cols(int nt, int tpc = 2) {  // power of two >= 32 holding tpc accumulators of nt columns
@@ -104,9 +104,10 @@ __host__ __device__ inline TcSmem tc_smem_layout(int nt, int sa, int sb, int na 
     return L;
 }
 
-// WIDE = 1: up to 17 warps, one CTA per SM; WIDE = 0: up to 13 warps (two tiles x two issuers), two CTAs per SM
+// WIDE = 1: up to 17 warps, one CTA per SM; WIDE = 0: up to 13 warps (two tiles x two issuers), two CTAs per SM;
+// WIDE = 2: 11 warps (two tiles, one issuer each), three CTAs per SM (narrow layers: small weight stages)
 template <int NA, int LPR, int WIDE>
-__global__ void __launch_bounds__(WIDE ? kTcMaxThreads : 13 * 32, WIDE ? 1 : 2)
+__global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 32 : 13 * 32), WIDE == 1 ? 1 : (WIDE == 2 ? 3 : 2))
     k_conv_tc(Gather gt, const float *__restrict__ in, int64_t ld_in, float *__restrict__ out, int64_t ld_out,
               const float *__restrict__ packed, int c_in, int NT, int SA, int SB, int TPC, int GW, int ACC,
               double *__restrict__ stats) {
@@ -457,15 +458,19 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
     //   acc  issuer warps / TMEM accumulator sets per tile (the issue chain of a stage-step is the serial bottleneck)
     //   sa   A stages per CTA (sx = sa / tpc per tile), sb weight stages; acc and the gather warps per tile (gw) must
     //        divide sx, acc must divide sb: every stage then always meets the same producer and consumer warp
-    static const int want_ctas = env_int("MOPA_TC_CTAS", 2), want_sb = env_int("MOPA_TC_SB", 4), want_tpc = env_int("MOPA_TC_TPC", 0);
+    static const int want_ctas = env_int("MOPA_TC_CTAS", 3), want_sb = env_int("MOPA_TC_SB", 4), want_tpc = env_int("MOPA_TC_TPC", 0);
     static const int want_sa = env_int("MOPA_TC_SA", 0), want_na = env_int("MOPA_TC_NA", 0), want_acc = env_int("MOPA_TC_ACC", 2);
     const int sms = num_sms();
     const int tpc = want_tpc ? want_tpc : (ceil_div(gt.n_out, kTcTM) > sms ? 2 : 1);
     const int na = want_na ? want_na : ((tpc == 1 && c_in >= 64 && ceil_div(gt.n_out, 128) <= sms) ? 2 : 1);
     bool two = want_ctas >= 2 && (nt <= 64 || tpc == 1) && ceil_div(gt.n_out, 128 * tpc) > sms;  // two CTAs per SM
+    // three CTAs per SM (MOPA_TC_CTAS=3): narrow layers of the large levels, two stages per tile, one issuer per tile
+    const bool three = want_ctas >= 3 && two && tpc == 2 && na == 1 && nt <= 32 && ceil_div(gt.n_out, 256) > 2 * sms &&
+                       (size_t)tc_smem_layout(nt, 4, 2, 1).total + 1024 <= (size_t)75 * 1024;
     int acc = 1, sb = 2, sa = 0;
     size_t cap = 0;
     for (;;) {
+        if (three) { acc = 1; sb = 2; sa = 4; cap = (size_t)75 * 1024; break; }
         cap = two ? (size_t)113 * 1024 : (size_t)226 * 1024;
         acc = want_acc >= 4 ? 4 : (want_acc >= 2 ? 2 : 1);
         while (acc > 1 && (tc_tmem_cols(nt, tpc * acc) > (two ? 256 : 512) || 32 * (9 + tpc * acc) > (two ? 13 * 32 : kTcMaxThreads))) acc >>= 1;
@@ -491,6 +496,8 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
         MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<2, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         return 0;
     }));
     const int sx = sa / tpc;
@@ -500,6 +507,14 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
     const unsigned threads = 32u * (unsigned)(9 + tpc * acc);
     dim3 grid((unsigned)ceil_div(gt.n_out, 128 * tpc));
     const bool wide = threads > 13 * 32;
+    if (three) {  // 11 warps, <= 75 KB: three CTAs per SM
+        if (c_in == 16)
+            k_conv_tc<1, 4, 2><<<grid, threads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc, gw, acc, stats);
+        else
+            k_conv_tc<1, 8, 2><<<grid, threads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc, gw, acc, stats);
+        MOPA_LAUNCHED();
+        return 0;
+    }
 #define MOPA_TC_LAUNCH(NA_, LPR_)                                                                                         \
     do {                                                                                                                  \
         if (wide)                                                                                                         \

@@ -190,9 +190,9 @@ __global__ void __launch_bounds__(256) k_insert(const int64_t *__restrict__ coor
                                                 uint64_t *__restrict__ tab_keys, int32_t *__restrict__ tab_vals,
                                                 uint32_t mask, int32_t *__restrict__ slot_of,
                                                 uint64_t *__restrict__ key_of, int32_t *__restrict__ kidx,
-                                                int32_t *__restrict__ err) {
+                                                int32_t *__restrict__ err, const int32_t *__restrict__ n_dev) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || (n_dev && i >= *n_dev)) return;  // n: launch bound; *n_dev: the element count only the device knows
     uint64_t key;
     if (MODE == 0) {
         int64_t x, y, z, b = 0;
@@ -234,9 +234,10 @@ __global__ void __launch_bounds__(256) k_insert(const int64_t *__restrict__ coor
 
 __global__ void __launch_bounds__(256) k_flag_first(const int32_t *__restrict__ slot_of,
                                                     const int32_t *__restrict__ tab_vals, int64_t n,
-                                                    int32_t *__restrict__ flags) {
+                                                    int32_t *__restrict__ flags, const int32_t *__restrict__ n_dev) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (n_dev && i >= *n_dev) { flags[i] = 0; return; }
     int s = slot_of[i];
     flags[i] = (s >= 0 && tab_vals[s] == (int32_t)i) ? 1 : 0;
 }
@@ -256,9 +257,10 @@ __global__ void __launch_bounds__(256) k_assign_ids(const int32_t *__restrict__ 
 
 __global__ void __launch_bounds__(256) k_read_ids(const int32_t *__restrict__ slot_of,
                                                   const int32_t *__restrict__ tab_vals, int64_t n,
-                                                  int32_t *__restrict__ ids, int32_t *__restrict__ counts) {
+                                                  int32_t *__restrict__ ids, int32_t *__restrict__ counts,
+                                                  const int32_t *__restrict__ n_dev) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || (n_dev && i >= *n_dev)) return;
     int s = slot_of[i];
     int id = s >= 0 ? tab_vals[s] : -1;
     ids[i] = id;
@@ -272,10 +274,11 @@ static uint32_t table_capacity(int64_t n) {
 }
 
 // Builds the table + ids; *count_dev receives the number of unique keys. uniq_keys must hold n entries.
+// n: number of elements, or (n_dev != nullptr) an upper bound of it with the true count in *n_dev on the device.
 static int unique_first(int mode, const int64_t *coords, int ncols, int64_t spatial, const uint64_t *fine_keys,
                         int64_t n, uint64_t *tab_keys, int32_t *tab_vals, uint32_t cap, uint64_t *uniq_keys,
                         int32_t *ids, int32_t *kidx, int32_t *counts, int32_t *count_dev, int32_t *err_dev,
-                        cudaStream_t s) {
+                        cudaStream_t s, const int32_t *n_dev = nullptr) {
     MOPA_CUDA(cudaMemsetAsync(tab_keys, 0xFF, (size_t)cap * 8, s));
     MOPA_CUDA(cudaMemsetAsync(tab_vals, 0x7F, (size_t)cap * 4, s));
     if (n == 0) {
@@ -293,17 +296,17 @@ static int unique_first(int mode, const int64_t *coords, int ncols, int64_t spat
     unsigned g = (unsigned)ceil_div(n, 256);
     if (mode == 0)
         k_insert<0><<<g, 256, 0, s>>>(coords, ncols, spatial, nullptr, n, tab_keys, tab_vals, cap - 1, slot_of, key_of,
-                                      nullptr, err_dev);
+                                      nullptr, err_dev, n_dev);
     else
         k_insert<1><<<g, 256, 0, s>>>(nullptr, 0, 0, fine_keys, n, tab_keys, tab_vals, cap - 1, slot_of, key_of, kidx,
-                                      err_dev);
+                                      err_dev, n_dev);
     MOPA_LAUNCHED();
-    k_flag_first<<<g, 256, 0, s>>>(slot_of, tab_vals, n, flags);
+    k_flag_first<<<g, 256, 0, s>>>(slot_of, tab_vals, n, flags, n_dev);
     MOPA_LAUNCHED();
     MOPA_TRY(exclusive_scan(flags, rank, n, bsum, count_dev, s));
     k_assign_ids<<<g, 256, 0, s>>>(slot_of, flags, rank, key_of, n, tab_vals, uniq_keys);
     MOPA_LAUNCHED();
-    k_read_ids<<<g, 256, 0, s>>>(slot_of, tab_vals, n, ids, counts);
+    k_read_ids<<<g, 256, 0, s>>>(slot_of, tab_vals, n, ids, counts, n_dev);
     MOPA_LAUNCHED();
     MOPA_CUDA(cudaFreeAsync(slot_of, s));
     MOPA_CUDA(cudaFreeAsync(flags, s));
@@ -437,6 +440,7 @@ __global__ void k_rule_offsets(const int32_t *__restrict__ rank, const int32_t *
 
 // ------------------------------------------------------------------------------------------------ Metadata ops
 int ensure_subm(mopa_scn_metadata *m, int level, cudaStream_t s) {
+    MOPA_TRY(finish_levels(m, s));
     Level &L = m->levels[level];
     if (L.nbr) return 0;
     L.nbr_ld = round_up(L.V > 0 ? L.V : 1, 32);
@@ -455,39 +459,77 @@ static int read_back(mopa_scn_metadata *m, const int32_t *dev, int n_ints, cudaS
     return 0;
 }
 
-int ensure_down(mopa_scn_metadata *m, int level, cudaStream_t s) {
+static int cnt_block(mopa_scn_metadata *m, cudaStream_t s) {
+    if (m->cnt_dev) return 0;
+    MOPA_TRY(meta_alloc(m, (void **)&m->cnt_dev, 32 * 4, s));
+    MOPA_CUDA(cudaMemsetAsync(m->cnt_dev, 0, 32 * 4, s));
+    return 0;
+}
+
+// Hashes level + 1 (stride-2 parents of level's sites): table, coarse keys in id order, parent / kidx of every fine
+// site. No host round trip: when the fine level's site count is still device-only, its upper bound sizes the
+// allocations and the launches, and the kernels read the true count from cnt_dev. child / tile rulebooks (which need exact
+// row counts) follow in finish_levels.
+int ensure_down_async(mopa_scn_metadata *m, int level, cudaStream_t s) {
     if (m->levels[level].has_down) return 0;
     MOPA_CHECK((int)m->levels.size() == level + 1, "strided levels must be created in order");
+    MOPA_CHECK(level + 1 < 31, "too many levels");
     MOPA_CHECK(m->levels[level].spatial % 2 == 0, "input spatial size must be even for a size-2 stride-2 convolution");
+    MOPA_TRY(cnt_block(m, s));
     m->levels.emplace_back();
     Level &L = m->levels[level];
     Level &N = m->levels[level + 1];
     N.spatial = L.spatial / 2;
-    const int64_t Vf = L.V;
+    const bool pending = L.V < 0;
+    const int64_t Vf = pending ? L.V_bound : L.V;  // elements to launch / allocate for
+    N.V = -1;
+    N.V_bound = Vf;
     N.cap = table_capacity(Vf);
     MOPA_TRY(meta_alloc(m, (void **)&N.tab_keys, (size_t)N.cap * 8, s));
     MOPA_TRY(meta_alloc(m, (void **)&N.tab_vals, (size_t)N.cap * 4, s));
     MOPA_TRY(meta_alloc(m, (void **)&N.keys, (size_t)Vf * 8, s));
     MOPA_TRY(meta_alloc(m, (void **)&L.parent, (size_t)Vf * 4, s));
     MOPA_TRY(meta_alloc(m, (void **)&L.kidx, (size_t)Vf * 4, s));
-    int32_t *cnt;
-    MOPA_TRY(tmp_alloc((void **)&cnt, 8, s));
     MOPA_TRY(unique_first(1, nullptr, 0, 0, L.keys, Vf, N.tab_keys, N.tab_vals, N.cap, N.keys, L.parent, L.kidx, nullptr,
-                          cnt, cnt + 1, s));
-    MOPA_TRY(read_back(m, cnt, 1, s));
-    MOPA_CUDA(cudaFreeAsync(cnt, s));
-    N.V = m->pinned[0];
-    L.child_ld = round_up(N.V > 0 ? N.V : 1, 32);
-    MOPA_TRY(meta_alloc(m, (void **)&L.child, (size_t)8 * L.child_ld * 4, s));
-    MOPA_CUDA(cudaMemsetAsync(L.child, 0xFF, (size_t)8 * L.child_ld * 4, s));
-    if (Vf > 0) {
-        k_child_scatter<<<(unsigned)ceil_div(Vf, 256), 256, 0, s>>>(L.parent, L.kidx, Vf, L.child, L.child_ld);
-        MOPA_LAUNCHED();
-    }
-    MOPA_TRY(build_tile_lists(m, L.child, L.child_ld, nullptr, nullptr, N.V, Vf, 8, &L.tl_child, &L.tm_child, s));
-    MOPA_TRY(build_tile_lists(m, nullptr, 0, L.parent, L.kidx, Vf, N.V, 8, &L.tl_sel, &L.tm_sel, s));
+                          m->cnt_dev + level + 1, m->cnt_dev + 31, s, pending ? m->cnt_dev + level : nullptr));
+    if (m->pending_from < 0) m->pending_from = level + 1;
     L.has_down = true;
     return 0;
+}
+
+// ONE synchronisation for every level hashed since the last call: reads the site counts back, then builds the structures
+// that need exact row counts (child tables, tile rulebooks of the strided links).
+int finish_levels(mopa_scn_metadata *m, cudaStream_t s) {
+    if (m->pending_from < 0) return 0;
+    const int first = m->pending_from, n_lv = (int)m->levels.size();
+    MOPA_CUDA(cudaMemcpyAsync(m->pinned, m->cnt_dev, 32 * 4, cudaMemcpyDeviceToHost, s));
+    MOPA_CUDA(cudaStreamSynchronize(s));
+    m->pending_from = -1;
+    for (int l = first; l < n_lv; ++l)
+        if (m->levels[l].V < 0) m->levels[l].V = m->pinned[l];
+    MOPA_CHECK(m->pinned[31] == 0, "InputLayer: coordinates outside [0, spatial_size) or batch index outside [0, 65535)");
+    for (int l = (first > 0 ? first - 1 : 0); l + 1 < n_lv; ++l) {
+        Level &L = m->levels[l];
+        Level &N = m->levels[l + 1];
+        if (!L.has_down || L.child) continue;
+        const int64_t Vf = L.V;
+        L.child_ld = round_up(N.V > 0 ? N.V : 1, 32);
+        MOPA_TRY(meta_alloc(m, (void **)&L.child, (size_t)8 * L.child_ld * 4, s));
+        MOPA_CUDA(cudaMemsetAsync(L.child, 0xFF, (size_t)8 * L.child_ld * 4, s));
+        if (Vf > 0) {
+            k_child_scatter<<<(unsigned)ceil_div(Vf, 256), 256, 0, s>>>(L.parent, L.kidx, Vf, L.child, L.child_ld);
+            MOPA_LAUNCHED();
+        }
+        MOPA_TRY(build_tile_lists(m, L.child, L.child_ld, nullptr, nullptr, N.V, Vf, 8, &L.tl_child, &L.tm_child, s));
+        MOPA_TRY(build_tile_lists(m, nullptr, 0, L.parent, L.kidx, Vf, N.V, 8, &L.tl_sel, &L.tm_sel, s));
+    }
+    return 0;
+}
+
+int ensure_down(mopa_scn_metadata *m, int level, cudaStream_t s) {
+    if (m->levels[level].has_down && m->pending_from < 0) return 0;
+    MOPA_TRY(ensure_down_async(m, level, s));
+    return finish_levels(m, s);
 }
 
 // compact a (K, ld) table with V columns into pairs on the HOST side buffers (inspection only; synchronises)
@@ -526,7 +568,7 @@ static int rulebook_to_host(mopa_scn_metadata *m, const int32_t *table, int64_t 
 }
 
 int set_locations(mopa_scn_metadata *m, int64_t spatial_size, const int64_t *coords, int64_t n, int ncols,
-                  int coords_on_device, cudaStream_t s) {
+                  int coords_on_device, cudaStream_t s, bool defer_sync) {
     MOPA_CHECK(m != nullptr, "null metadata");
     MOPA_CHECK(ncols == 3 || ncols == 4, "coords must have 3 or 4 columns");
     MOPA_CHECK(spatial_size > 0 && spatial_size <= 65536, "spatial_size must be in (0, 65536]");
@@ -553,15 +595,14 @@ int set_locations(mopa_scn_metadata *m, int64_t spatial_size, const int64_t *coo
     MOPA_TRY(meta_alloc(m, (void **)&m->p2v, (size_t)n * 4, s));
     MOPA_TRY(meta_alloc(m, (void **)&m->csr_off, (size_t)(n + 1) * 4, s));
     MOPA_TRY(meta_alloc(m, (void **)&m->csr_rows, (size_t)n * 4, s));
-    int32_t *counts, *cnt, *tmp_rows, *bsum;
+    int32_t *counts, *tmp_rows, *bsum;
+    MOPA_TRY(cnt_block(m, s));
     MOPA_TRY(tmp_alloc((void **)&counts, (size_t)(n + 1) * 4, s));
-    MOPA_TRY(tmp_alloc((void **)&cnt, 8, s));
     MOPA_TRY(tmp_alloc((void **)&tmp_rows, (size_t)n * 4, s));
     MOPA_TRY(tmp_alloc((void **)&bsum, (size_t)ceil_div(n + 1, 1024) * 4, s));
     MOPA_CUDA(cudaMemsetAsync(counts, 0, (size_t)(n + 1) * 4, s));
-    MOPA_CUDA(cudaMemsetAsync(cnt, 0, 8, s));
     MOPA_TRY(unique_first(0, dcoords, ncols, spatial_size, nullptr, n, L.tab_keys, L.tab_vals, L.cap, L.keys, m->p2v,
-                          nullptr, counts, cnt, cnt + 1, s));
+                          nullptr, counts, m->cnt_dev, m->cnt_dev + 31, s));
     if (n > 0) {
         // CSR offsets over the (n + 1)-long zero-padded count array: off[v] valid for v <= V0, off[V0] = n
         MOPA_TRY(exclusive_scan(counts, m->csr_off, n + 1, bsum, nullptr, s));
@@ -574,15 +615,14 @@ int set_locations(mopa_scn_metadata *m, int64_t spatial_size, const int64_t *coo
     } else {
         MOPA_CUDA(cudaMemsetAsync(m->csr_off, 0, 4, s));
     }
-    MOPA_TRY(read_back(m, cnt, 2, s));
-    L.V = m->pinned[0];
-    int err = m->pinned[1];
     MOPA_CUDA(cudaFreeAsync(counts, s));
-    MOPA_CUDA(cudaFreeAsync(cnt, s));
     MOPA_CUDA(cudaFreeAsync(tmp_rows, s));
     MOPA_CUDA(cudaFreeAsync(bsum, s));
     if (staged) MOPA_CUDA(cudaFreeAsync(staged, s));
-    MOPA_CHECK(err == 0, "InputLayer: coordinates outside [0, spatial_size) or batch index outside [0, 65535)");
+    L.V = -1;  // device-only until finish_levels
+    L.V_bound = n;
+    m->pending_from = 0;
+    if (!defer_sync) MOPA_TRY(finish_levels(m, s));
     return 0;
 }
 

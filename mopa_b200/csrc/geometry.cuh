@@ -8,7 +8,8 @@ namespace mopa {
 
 struct Level {
     int64_t spatial = 0;
-    int64_t V = 0;                 // active sites
+    int64_t V = 0;                 // active sites (host value; -1 while only the device knows it, see cnt_dev)
+    int64_t V_bound = 0;           // upper bound used for allocations / grids of this level's hashing structures
     uint64_t *keys = nullptr;      // [V] packed site keys, id order
     uint64_t *tab_keys = nullptr;  // open-addressing table: key -> id
     int32_t *tab_vals = nullptr;
@@ -48,6 +49,10 @@ struct mopa_scn_metadata {
     cudaStream_t last_stream = nullptr;
     int32_t *pinned = nullptr;  // small host staging block for counts
     cudaEvent_t geom_done = nullptr;  // recorded on the geometry stream when grids/tables are complete
+    // device-side site counts: cnt_dev[l] = V of level l, cnt_dev[31] = coordinate error flag. Levels are hashed back to
+    // back with upper-bound sizes and the counts come back in ONE read (finish_levels), not one per level.
+    int32_t *cnt_dev = nullptr;
+    int pending_from = -1;  // first level whose V is still device-only, or -1
 
     int level_of(int64_t spatial) const {
         for (size_t l = 0; l < levels.size(); ++l)
@@ -75,7 +80,7 @@ struct Gather {
 
 int meta_alloc(mopa_scn_metadata *m, void **p, size_t bytes, cudaStream_t s);
 int set_locations(mopa_scn_metadata *m, int64_t spatial_size, const int64_t *coords, int64_t n, int ncols,
-                  int coords_on_device, cudaStream_t s);
+                  int coords_on_device, cudaStream_t s, bool defer_sync = false);
 int conv_apply(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *weight,
                const float *packed, int n_in0, int n_out0, int transpose, int flip, int precision, cudaStream_t s,
                double *stats = nullptr, bool *stats_done = nullptr);
@@ -127,4 +132,6 @@ int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, con
 size_t bn_workspace_bytes(int planes);
 int ensure_subm(mopa_scn_metadata *m, int level, cudaStream_t s);
 int ensure_down(mopa_scn_metadata *m, int level, cudaStream_t s);
+int ensure_down_async(mopa_scn_metadata *m, int level, cudaStream_t s);  // hashes level + 1 without a host round trip
+int finish_levels(mopa_scn_metadata *m, cudaStream_t s);                  // ONE synchronisation: all pending counts
 }  // namespace mopa

@@ -244,8 +244,11 @@ int mopa_scn_Program_prepare(mopa_scn_program *p, mopa_scn_metadata *m, const in
         MOPA_CUDA(cudaEventRecord(m->geom_done, main));
         MOPA_CUDA(cudaStreamWaitEvent(gs, m->geom_done, 0));
     }
-    MOPA_TRY(set_locations(m, p->spatial, coords, n, ncols, coords_on_device, gs));
-    for (int l = 0; l + 1 < p->n_levels; ++l) MOPA_TRY(ensure_down(m, l, gs));
+    // the whole pyramid is hashed back to back; ONE host round trip brings every level's site count (and the coordinate
+    // error flag) back, instead of one per level
+    MOPA_TRY(set_locations(m, p->spatial, coords, n, ncols, coords_on_device, gs, /*defer_sync=*/true));
+    for (int l = 0; l + 1 < p->n_levels; ++l) MOPA_TRY(ensure_down_async(m, l, gs));
+    MOPA_TRY(finish_levels(m, gs));
     bool need_subm[32] = {false};
     for (const POp &o : p->ops)
         if (o.type == OP_SUBM) need_subm[o.level_in] = true;

@@ -3,9 +3,11 @@
 One process per GPU; every rank holds a full UNetSCN replica and its own scans (a scan is never split); BatchNorm
 statistics stay per rank, as in the reference's single-GPU batch of 8. The only exchange is one gradient all-reduce
 (mean) per optimizer step over NCCL/NVLink: all gradients are packed into ONE flat fp32 bucket (~10.8 MB for UNetSCN)
-by a single multi-tensor copy, so the collective is one call and MoPA's two backward() calls per step
-(train_xmuda_mopa.py:417-418,578-579) reduce once. (Pointing .grad at bucket slices BEFORE backward made autograd run
-one small add kernel per parameter, 78 launches per step; with .grad = None autograd just keeps the produced tensor.)
+so the collective is one call and MoPA's two backward() calls per step (train_xmuda_mopa.py:417-418,578-579) reduce once.
+With bucket.attach() the compiled UNetSCN backward writes each gradient straight into its slice of the bucket (the first
+backward of a step; later ones are added to it by autograd), so nothing is packed; parameters of other modules are
+packed by one multi-tensor copy. (Pointing .grad at bucket slices BEFORE backward made autograd run one small add kernel
+per parameter, 78 launches per step; with .grad = None autograd just keeps the tensor the backward returns.)
 """
 import torch
 import torch.distributed as dist
@@ -36,6 +38,17 @@ class FlatGradBucket:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
         self.zero()
+
+    def attach(self):
+        """Let mopa_b200.scn's compiled backward write gradients straight into this bucket's slices (no pack copy): see
+        scn.compiler.register_grad_views. Parameters of other modules (e.g. nn.Linear heads) still go through pack()."""
+        from .scn import compiler
+        compiler.register_grad_views({p: v for p, v in zip(self.params, self.views)})
+        return self
+
+    def detach(self):
+        from .scn import compiler
+        compiler.unregister_grad_views(self.params)
 
     def zero(self):
         for p in self.params:

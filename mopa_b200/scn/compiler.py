@@ -156,6 +156,30 @@ class CompiledProgram:
 
 _programs = weakref.WeakKeyDictionary()
 
+# parameter -> caller-owned gradient view (mopa_b200.parallel.FlatGradBucket.attach): when a parameter has no .grad yet, the
+# compiled backward writes its gradient straight into that view, so a data-parallel step needs no gather / pack of the
+# 78 gradient tensors before its single all-reduce
+_grad_views = {}  # id(parameter) -> (weakref to the parameter, view); keyed by identity (tensors do not compare by ==)
+
+
+def register_grad_views(mapping):
+    """mapping: parameter -> float32 tensor view of the same shape (e.g. slices of one flat all-reduce buffer)."""
+    for p, v in mapping.items():
+        if v.shape != p.shape or v.dtype != torch.float32 or not v.is_contiguous():
+            raise _lib.ScnError("gradient views must be contiguous float32 tensors of the parameter's shape")
+        key = id(p)
+        _grad_views[key] = (weakref.ref(p, lambda _, k=key: _grad_views.pop(k, None)), v)
+
+
+def unregister_grad_views(params):
+    for p in params:
+        _grad_views.pop(id(p), None)
+
+
+def _grad_view_of(t):
+    entry = _grad_views.get(id(t))
+    return entry[1] if entry is not None and entry[0]() is t else None
+
 
 def compiled_for(root):
     """CompiledProgram for this module tree, or None if it cannot / should not be compiled."""
@@ -235,16 +259,23 @@ class _ProgramFunction(Function):
         trainable_idx = ctx.read_idx
         sizes = [tensors[i].numel() for i in trainable_idx]
         with torch.cuda.device(dev):
-            flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            # gradients land either in the caller's registered views (first backward of a step: .grad is None, autograd
+            # keeps the tensor we return) or in one fresh flat buffer (accumulating backward: autograd adds it to .grad)
+            direct = [_grad_view_of(tensors[i]) if tensors[i].grad is None else None for i in trainable_idx]
+            direct = [v if (v is not None and v.device == dev) else None for v in direct]
+            flat = torch.empty(sum(sz for sz, v in zip(sizes, direct) if v is None), dtype=torch.float32, device=dev)
             grads, ptrs, off = [], [None] * len(tensors), 0
             for j, (i, sz) in enumerate(zip(trainable_idx, sizes)):
-                if need[4 + j]:
-                    g = flat[off:off + sz].view_as(tensors[i])
-                    ptrs[i] = g.data_ptr()
-                    grads.append(g)
-                else:
+                if not need[4 + j]:
                     grads.append(None)
-                off += sz
+                    continue
+                if direct[j] is not None:
+                    g = direct[j]
+                else:
+                    g = flat[off:off + sz].view_as(tensors[i])
+                    off += sz
+                ptrs[i] = g.data_ptr()
+                grads.append(g)
             params = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() if t is not None else None for t in tensors])
             pgrads = (ctypes.c_void_p * len(tensors))(*ptrs)
             grad_arena = torch.empty(ctx.sizes[0], dtype=torch.uint8, device=dev)

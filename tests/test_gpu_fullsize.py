@@ -16,7 +16,9 @@ from tests.helpers import rel_err
 pytestmark = pytest.mark.gpu
 
 # (forward max-abs / max-magnitude, gradient rel-L2, gradient cosine) per precision mode; see module docstring
-BARS = {"fp32": (2e-4, 2e-2, 0.9995), "tf32": (2e-2, 0.2, 0.98)}
+# measured worst case over the 78 tensors (profiles/r02_grad_errors*.txt): fp32 mode forward 1.3e-5, rel-L2 9.9e-3, cos 0.99995;
+# tf32 mode forward 1.2e-3, rel-L2 0.132, cos 0.9915 (the float32 ORACLE itself: 6.3e-4)
+BARS = {"fp32": (5e-5, 3e-2, 0.9998), "tf32": (5e-3, 0.27, 0.98)}
 
 
 @pytest.fixture(scope="module")

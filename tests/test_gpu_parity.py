@@ -3,9 +3,10 @@
 Bars (BASELINE.json north_star): voxel maps and rulebooks BIT-EXACT; features and gradients, as max |diff| over the
 tensor's max magnitude against the float64 oracle:
   per layer (forward, d_input, d_weight):  fp32 mode (3xTF32 split, the default) 5e-5,  tf32 mode (opt-in) 5e-3
-  whole UNetSCN forward (26 BN + 26 convs): fp32 mode 5e-4,                tf32 mode 5e-2   (measured 1e-5 / 1.3e-3)
-  whole UNetSCN gradients, per parameter tensor, relative L2 + cosine:
-      fp32 mode  rel-L2 <= 6e-2, cosine >= 0.999      tf32 mode  rel-L2 <= 0.2, cosine >= 0.98
+  whole UNetSCN forward (26 BN + 26 convs): fp32 mode 1e-4,                tf32 mode 1e-2   (measured 1.3e-5 / 1.2e-3)
+  whole UNetSCN gradients, per parameter tensor, relative L2 + cosine (bars <= 3x the measured worst tensor of
+  profiles/r02_grad_errors.txt: fp32 mode 9.9e-3 / 0.99995, tf32 mode 0.132 / 0.9915, float32 oracle 6.3e-4):
+      fp32 mode  rel-L2 <= 3e-2, cosine >= 0.9995     tf32 mode  rel-L2 <= 0.2, cosine >= 0.98
 The end-to-end gradient bars are loose because the random-init network's backward pass is ill conditioned, not
 because a kernel is: the float32 ORACLE itself sits 4e-3 (rel-L2) from the float64 oracle at 71k points (26 BatchNorm
 backward passes subtract the dominant components of the incoming gradient), i.e. a ~1e4 amplification of fp32 rounding.
@@ -21,7 +22,7 @@ from tests.helpers import random_cloud, rel_err, small_batch
 pytestmark = pytest.mark.gpu
 
 TOL_LAYER = {"fp32": 5e-5, "tf32": 5e-3}
-TOL_NET = {"fp32": 5e-4, "tf32": 5e-2}
+TOL_NET = {"fp32": 1e-4, "tf32": 1e-2}  # measured at full scan size: 1.3e-5 / 1.2e-3 (profiles/r02_grad_errors.txt)
 
 
 @pytest.fixture(scope="module")
@@ -246,8 +247,8 @@ def test_fused_batchnorm_matches_two_kernel_path_bitwise_inputs(scn, planes, mon
     feats = (torch.randn(coords.shape[0], planes, generator=torch.Generator().manual_seed(4)) * 3 + 1.5)
     res = {}
     for mode in ("1", "0"):
-        monkeypatch.setenv("MOPA_SCN_NO_BNFUSED", mode)
-        x, f = _input(scn, coords, feats, size=64)
+        monkeypatch.setenv("MOPA_SCN_NO_BNFUSED", mode)  # "0": the cooperative kernel (its size threshold is read once per
+        x, f = _input(scn, coords, feats, size=64)       # process: conftest.py exports MOPA_SCN_BN_FUSED_MIN=0 for the tests)
         bn = scn.BatchNormLeakyReLU(planes, leakiness=0.1).cuda()
         outs = []
         for it in range(3):
@@ -297,7 +298,7 @@ def _rel_l2_cos(a, b):
     return float((a - b).norm() / b.norm()), float(torch.dot(a, b) / (a.norm() * b.norm()))
 
 
-GRAD_NET = {"fp32": (6e-2, 0.999), "tf32": (0.2, 0.98)}
+GRAD_NET = {"fp32": (3e-2, 0.9995), "tf32": (0.2, 0.98)}  # measured worst tensor: 9.9e-3 / 0.132 (profiles/r02_grad_errors.txt)
 
 
 @pytest.mark.parametrize("mode", ["compiled", "eager"])

@@ -153,3 +153,25 @@ def test_oracle_ed_state_uses_the_reference_key_layout():
     st = so.make_ed_state(3)
     net = UNetSCN_ED(3)
     assert {k: tuple(v.shape) for k, v in st.items()} == {k: tuple(v.shape) for k, v in net.state_dict().items()}
+
+
+def test_compiled_for_caches_and_respects_eager_switch(monkeypatch):
+    """Host logic of the executor selection (no GPU needed): one CompiledProgram per module tree, rebuilt when the tree
+    changes, none under MOPA_SCN_EAGER=1 or with mixed train/eval BatchNorms; gradient views are keyed by parameter identity."""
+    from mopa_b200.unet_scn import UNetSCN
+    from mopa_b200.scn import compiler
+    net = UNetSCN(1)
+    a = compiler.compiled_for(net.sparseModel)
+    assert a is not None and compiler.compiled_for(net.sparseModel) is a
+    net.sparseModel[3].eval()
+    assert compiler.compiled_for(net.sparseModel) is None  # mixed modes -> module-by-module path
+    net.train()
+    monkeypatch.setenv("MOPA_SCN_EAGER", "1")
+    assert compiler.compiled_for(net.sparseModel) is None
+    monkeypatch.delenv("MOPA_SCN_EAGER")
+    params = list(net.parameters())
+    views = {p: torch.zeros_like(p) for p in params[:3]}
+    compiler.register_grad_views(views)
+    assert compiler._grad_view_of(params[0]) is views[params[0]] and compiler._grad_view_of(params[5]) is None
+    compiler.unregister_grad_views(params[:3])
+    assert compiler._grad_view_of(params[0]) is None
