@@ -419,8 +419,9 @@ def run_ours(a):
             "all_reduce_us_median": ar_us,
             "fp32_ms_per_step": (1e3 * fp32["sec"] / max(5, min(20, a.steps // 5))) if fp32 else None,
             "gpu_launches": res["launches"], "clocks": clocks, "roofline": roof, "geometry": geo, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -270,8 +270,8 @@ class _ProgramFunction(Function):
                     grads.append(None)
                     continue
                 if direct[j] is not None:
-                    g = direct[j]
-                else:
+                    g = direct[j].view_as(direct[j])  # a fresh tensor object: autograd only keeps (instead of cloning) a
+                else:                                 # gradient nobody else holds a reference to
                     g = flat[off:off + sz].view_as(tensors[i])
                     off += sz
                 ptrs[i] = g.data_ptr()
