@@ -232,27 +232,56 @@ __global__ void __launch_bounds__(256) k_insert(const int64_t *__restrict__ coor
     key_of[i] = key;
 }
 
-__global__ void __launch_bounds__(256) k_flag_first(const int32_t *__restrict__ slot_of,
-                                                    const int32_t *__restrict__ tab_vals, int64_t n,
-                                                    int32_t *__restrict__ flags, const int32_t *__restrict__ n_dev) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (n_dev && i >= *n_dev) { flags[i] = 0; return; }
-    int s = slot_of[i];
-    flags[i] = (s >= 0 && tab_vals[s] == (int32_t)i) ? 1 : 0;
-}
-
-// elements that are a first occurrence publish their id into the slot and their key into the id-ordered key list
-__global__ void __launch_bounds__(256) k_assign_ids(const int32_t *__restrict__ slot_of,
-                                                    const int32_t *__restrict__ flags,
-                                                    const int32_t *__restrict__ rank,
-                                                    const uint64_t *__restrict__ key_of, int64_t n,
-                                                    int32_t *__restrict__ tab_vals, uint64_t *__restrict__ uniq_keys) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !flags[i]) return;
-    int id = rank[i];
-    tab_vals[slot_of[i]] = id;
-    uniq_keys[id] = key_of[i];
+// k_flag_first + exclusive scan + k_assign_ids in ONE pass (decoupled look-back over 1024-element blocks): element i is a
+// first occurrence iff its slot's first-index entry equals i; its id is the number of first occurrences before it; the id
+// goes into tab_ids[slot] (a separate array: tab_first is still being read by other blocks) and its key into uniq_keys[id].
+// status[b]: bits 63..62 = 1 (block aggregate published) / 2 (inclusive prefix published), low bits = the value; blocks take
+// their index from an atomic ticket, so a block only ever waits for blocks that have already started.
+__global__ void __launch_bounds__(1024) k_unique_scan(const int32_t *__restrict__ slot_of, const int32_t *__restrict__ tab_first,
+                                                      const uint64_t *__restrict__ key_of, int64_t n,
+                                                      const int32_t *__restrict__ n_dev, int32_t *__restrict__ tab_ids,
+                                                      uint64_t *__restrict__ uniq_keys, int32_t *__restrict__ count_out,
+                                                      unsigned long long *__restrict__ status, unsigned int *__restrict__ ticket) {
+    __shared__ int s_bid, s_prefix, s_total;
+    if (threadIdx.x == 0) s_bid = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int bid = s_bid;
+    const int64_t n_eff = n_dev ? min(n, (int64_t)*n_dev) : n;
+    const int64_t i = (int64_t)bid * 1024 + threadIdx.x;
+    int slot = -1, flag = 0;
+    if (i < n_eff) {
+        slot = slot_of[i];
+        flag = (slot >= 0 && tab_first[slot] == (int32_t)i) ? 1 : 0;
+    }
+    const int e = block_exclusive_scan_1024(flag, &s_total);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long total = (unsigned long long)s_total;
+        unsigned long long prefix = 0;
+        if (bid == 0) {
+            __threadfence();
+            atomicExch(status, (2ull << 62) | total);
+        } else {
+            __threadfence();
+            atomicExch(status + bid, (1ull << 62) | total);
+            for (int j = bid - 1; j >= 0; --j) {
+                unsigned long long v;
+                do { v = *(volatile unsigned long long *)(status + j); } while ((v >> 62) == 0);
+                prefix += v & ((1ull << 62) - 1);
+                if ((v >> 62) == 2) break;
+            }
+            __threadfence();
+            atomicExch(status + bid, (2ull << 62) | (prefix + total));
+        }
+        s_prefix = (int)prefix;
+        if ((int64_t)(bid + 1) * 1024 >= n) *count_out = (int)(prefix + total);  // the last block of the launch
+    }
+    __syncthreads();
+    if (flag) {
+        const int id = s_prefix + e;
+        tab_ids[slot] = id;
+        uniq_keys[id] = key_of[i];
+    }
 }
 
 __global__ void __launch_bounds__(256) k_read_ids(const int32_t *__restrict__ slot_of,
@@ -275,44 +304,43 @@ static uint32_t table_capacity(int64_t n) {
 
 // Builds the table + ids; *count_dev receives the number of unique keys. uniq_keys must hold n entries.
 // n: number of elements, or (n_dev != nullptr) an upper bound of it with the true count in *n_dev on the device.
+// Three kernels: hash insert (atomicCAS key, atomicMin first index), fused flag / scan / id assignment, id read-back.
 static int unique_first(int mode, const int64_t *coords, int ncols, int64_t spatial, const uint64_t *fine_keys,
                         int64_t n, uint64_t *tab_keys, int32_t *tab_vals, uint32_t cap, uint64_t *uniq_keys,
                         int32_t *ids, int32_t *kidx, int32_t *counts, int32_t *count_dev, int32_t *err_dev,
                         cudaStream_t s, const int32_t *n_dev = nullptr) {
     MOPA_CUDA(cudaMemsetAsync(tab_keys, 0xFF, (size_t)cap * 8, s));
-    MOPA_CUDA(cudaMemsetAsync(tab_vals, 0x7F, (size_t)cap * 4, s));
     if (n == 0) {
         MOPA_CUDA(cudaMemsetAsync(count_dev, 0, 4, s));
         return 0;
     }
-    int32_t *slot_of, *flags, *rank, *bsum;
+    int32_t *slot_of, *tab_first;
     uint64_t *key_of;
-    int64_t nb = ceil_div(n, 1024);
+    unsigned long long *status;
+    const int64_t nb = ceil_div(n, 1024);
     MOPA_TRY(tmp_alloc((void **)&slot_of, n * 4, s));
-    MOPA_TRY(tmp_alloc((void **)&flags, n * 4, s));
-    MOPA_TRY(tmp_alloc((void **)&rank, n * 4, s));
-    MOPA_TRY(tmp_alloc((void **)&bsum, nb * 4, s));
+    MOPA_TRY(tmp_alloc((void **)&tab_first, (size_t)cap * 4, s));
     MOPA_TRY(tmp_alloc((void **)&key_of, n * 8, s));
+    MOPA_TRY(tmp_alloc((void **)&status, (size_t)(nb + 1) * 8, s));
+    MOPA_CUDA(cudaMemsetAsync(tab_first, 0x7F, (size_t)cap * 4, s));
+    MOPA_CUDA(cudaMemsetAsync(status, 0, (size_t)(nb + 1) * 8, s));  // last entry: the block ticket
     unsigned g = (unsigned)ceil_div(n, 256);
     if (mode == 0)
-        k_insert<0><<<g, 256, 0, s>>>(coords, ncols, spatial, nullptr, n, tab_keys, tab_vals, cap - 1, slot_of, key_of,
+        k_insert<0><<<g, 256, 0, s>>>(coords, ncols, spatial, nullptr, n, tab_keys, tab_first, cap - 1, slot_of, key_of,
                                       nullptr, err_dev, n_dev);
     else
-        k_insert<1><<<g, 256, 0, s>>>(nullptr, 0, 0, fine_keys, n, tab_keys, tab_vals, cap - 1, slot_of, key_of, kidx,
+        k_insert<1><<<g, 256, 0, s>>>(nullptr, 0, 0, fine_keys, n, tab_keys, tab_first, cap - 1, slot_of, key_of, kidx,
                                       err_dev, n_dev);
     MOPA_LAUNCHED();
-    k_flag_first<<<g, 256, 0, s>>>(slot_of, tab_vals, n, flags, n_dev);
-    MOPA_LAUNCHED();
-    MOPA_TRY(exclusive_scan(flags, rank, n, bsum, count_dev, s));
-    k_assign_ids<<<g, 256, 0, s>>>(slot_of, flags, rank, key_of, n, tab_vals, uniq_keys);
+    k_unique_scan<<<(unsigned)nb, 1024, 0, s>>>(slot_of, tab_first, key_of, n, n_dev, tab_vals, uniq_keys, count_dev, status,
+                                               reinterpret_cast<unsigned int *>(status + nb));
     MOPA_LAUNCHED();
     k_read_ids<<<g, 256, 0, s>>>(slot_of, tab_vals, n, ids, counts, n_dev);
     MOPA_LAUNCHED();
     MOPA_CUDA(cudaFreeAsync(slot_of, s));
-    MOPA_CUDA(cudaFreeAsync(flags, s));
-    MOPA_CUDA(cudaFreeAsync(rank, s));
-    MOPA_CUDA(cudaFreeAsync(bsum, s));
+    MOPA_CUDA(cudaFreeAsync(tab_first, s));
     MOPA_CUDA(cudaFreeAsync(key_of, s));
+    MOPA_CUDA(cudaFreeAsync(status, s));
     return 0;
 }
 
@@ -341,35 +369,7 @@ __global__ void __launch_bounds__(256) k_csr_order(const int32_t *__restrict__ p
     rows[beg + r] = (int32_t)i;
 }
 
-// ------------------------------------------------------------------------------------------------ submanifold table
-// grid (ceil(V / 256), 27): one thread per (offset, site); writes are coalesced along the site axis.
-__global__ void __launch_bounds__(256) k_subm_table(const uint64_t *__restrict__ keys, int64_t V, int spatial,
-                                                    const uint64_t *__restrict__ tab_keys,
-                                                    const int32_t *__restrict__ tab_vals, uint32_t mask,
-                                                    int32_t *__restrict__ nbr, int64_t ld) {
-    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= V) return;
-    const int k = blockIdx.y;
-    const int dx = k / 9 - 1, dy = (k / 3) % 3 - 1, dz = k % 3 - 1;
-    int x, y, z, b;
-    unpack_key(keys[o], x, y, z, b);
-    x += dx; y += dy; z += dz;
-    int id = -1;
-    if (k == 13) {
-        id = (int)o;
-    } else if (x >= 0 && y >= 0 && z >= 0 && x < spatial && y < spatial && z < spatial) {
-        uint64_t q = pack_key((uint32_t)x, (uint32_t)y, (uint32_t)z, (uint32_t)b);
-        uint32_t s = hash_key(q) & mask;
-        while (true) {
-            uint64_t cur = __ldg(tab_keys + s);
-            if (cur == q) { id = __ldg(tab_vals + s); break; }
-            if (cur == kEmptyKey) break;
-            s = (s + 1) & mask;
-        }
-    }
-    nbr[(int64_t)k * ld + o] = id;
-}
-
+// ------------------------------------------------------------------------------------------------ strided links
 __global__ void __launch_bounds__(256) k_child_scatter(const int32_t *__restrict__ parent,
                                                        const int32_t *__restrict__ kidx, int64_t Vf,
                                                        int32_t *__restrict__ child, int64_t ld) {
@@ -396,6 +396,48 @@ __global__ void __launch_bounds__(128) k_tile_lists(const int32_t *__restrict__ 
     int rank = __popc(m & ((1u << lane) - 1u));
     for (int w = 0; w < warp; ++w) rank += __popc(wm[w]);
     const int64_t slot = t * K + k;
+    if (id >= 0) tl[(slot << 7) + rank] = id | (r << kTileRowShift);
+    if (r == 0) tm[slot] = make_uint4(wm[0], wm[1], wm[2], wm[3]);
+}
+
+// Submanifold level in ONE kernel: grid (tiles of 128 sites, 27), 128 threads: thread r probes the hash grid for the
+// neighbour of site 128 t + r at offset k, writes the dense table entry (the fp32-mode and small-channel kernels read it)
+// and the block compacts the hits into the tile rulebook, as k_tile_lists does from a finished table.
+__global__ void __launch_bounds__(128) k_subm_tiles(const uint64_t *__restrict__ keys, int64_t V, int spatial,
+                                                    const uint64_t *__restrict__ tab_keys, const int32_t *__restrict__ tab_vals,
+                                                    uint32_t mask, int32_t *__restrict__ nbr, int64_t ld,
+                                                    int32_t *__restrict__ tl, uint4 *__restrict__ tm) {
+    __shared__ uint32_t wm[4];
+    const int r = threadIdx.x, lane = r & 31, warp = r >> 5, k = blockIdx.y;
+    const int64_t t = blockIdx.x, o = t * kTileRows + r;
+    int id = -1;
+    if (o < V) {
+        if (k == 13) {
+            id = (int)o;
+        } else {
+            const int dx = k / 9 - 1, dy = (k / 3) % 3 - 1, dz = k % 3 - 1;
+            int x, y, z, b;
+            unpack_key(keys[o], x, y, z, b);
+            x += dx; y += dy; z += dz;
+            if (x >= 0 && y >= 0 && z >= 0 && x < spatial && y < spatial && z < spatial) {
+                const uint64_t q = pack_key((uint32_t)x, (uint32_t)y, (uint32_t)z, (uint32_t)b);
+                uint32_t s = hash_key(q) & mask;
+                while (true) {
+                    const uint64_t cur = __ldg(tab_keys + s);
+                    if (cur == q) { id = __ldg(tab_vals + s); break; }
+                    if (cur == kEmptyKey) break;
+                    s = (s + 1) & mask;
+                }
+            }
+        }
+        nbr[(int64_t)k * ld + o] = id;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, id >= 0);
+    if (lane == 0) wm[warp] = m;
+    __syncthreads();
+    int rank = __popc(m & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; ++w) rank += __popc(wm[w]);
+    const int64_t slot = t * 27 + k;
     if (id >= 0) tl[(slot << 7) + rank] = id | (r << kTileRowShift);
     if (r == 0) tm[slot] = make_uint4(wm[0], wm[1], wm[2], wm[3]);
 }
@@ -445,12 +487,14 @@ int ensure_subm(mopa_scn_metadata *m, int level, cudaStream_t s) {
     if (L.nbr) return 0;
     L.nbr_ld = round_up(L.V > 0 ? L.V : 1, 32);
     MOPA_TRY(meta_alloc(m, (void **)&L.nbr, (size_t)27 * L.nbr_ld * 4, s));
-    if (L.V > 0) {
-        dim3 grid((unsigned)ceil_div(L.V, 256), 27);
-        k_subm_table<<<grid, 256, 0, s>>>(L.keys, L.V, (int)L.spatial, L.tab_keys, L.tab_vals, L.cap - 1, L.nbr, L.nbr_ld);
-        MOPA_LAUNCHED();
-    }
-    return build_tile_lists(m, L.nbr, L.nbr_ld, nullptr, nullptr, L.V, L.V, 27, &L.tl_subm, &L.tm_subm, s);
+    MOPA_CHECK(L.V < ((int64_t)1 << kTileRowShift), "more than 2^25 active sites at one level: tile rulebook entries overflow");
+    const int64_t tiles = ceil_div(L.V > 0 ? L.V : 1, kTileRows);
+    MOPA_TRY(meta_alloc(m, (void **)&L.tl_subm, (size_t)tiles * 27 * kTileRows * 4, s));
+    MOPA_TRY(meta_alloc(m, (void **)&L.tm_subm, (size_t)tiles * 27 * sizeof(uint4), s));
+    k_subm_tiles<<<dim3((unsigned)tiles, 27), 128, 0, s>>>(L.keys, L.V, (int)L.spatial, L.tab_keys, L.tab_vals, L.cap - 1, L.nbr,
+                                                          L.nbr_ld, L.tl_subm, L.tm_subm);
+    MOPA_LAUNCHED();
+    return 0;
 }
 
 static int read_back(mopa_scn_metadata *m, const int32_t *dev, int n_ints, cudaStream_t s) {
