@@ -239,45 +239,51 @@ def roofline_pass(net, batches_dev, steps, peaks):
                               "frac": v[0] / v[1] / 1e9 / peak if v[1] else 0.0, "launches": v[2]} for k, v in cls.items()}}
 
 
-def geometry_pass(batches_dev, peaks, reps=10):
-    """Achieved HBM GB/s of the integer part of a forward (north_star: "achieved HBM GB/s for hashing"): voxel hashing +
-    first-occurrence ids + CSR lists, 6 strided levels, 7 neighbour tables and the tile rulebooks, timed with CUDA events
-    on the launching stream through the per-module entry points; algorithmic bytes per SURVEY.md 8(d):
-    voxelise N (32 + 4 + 4 Cin) + 4 V0 Cin; submanifold rulebook 16 V + 8 R per level; strided 16 Vl + 8 Vl + 16 Vl+1."""
-    import mopa_b200.scn as scn
-    from mopa_b200.scn import functional as F
+def geometry_pass(net, batches_dev, peaks, reps=10):
+    """Achieved HBM GB/s of the integer part of a forward (north_star: "achieved HBM GB/s for hashing"): exactly what a step
+    runs -- mopa_scn_Program_prepare: voxel hashing + first-occurrence ids + CSR lists, 6 strided levels, 7 neighbour tables
+    and the tile rulebooks, ONE host round trip for the counts -- timed with CUDA events on the caller's stream (which the
+    call makes wait for its geometry stream). Algorithmic bytes per SURVEY.md 8(d): voxelise N (32 + 4 + 4 Cin) + 4 V0 Cin;
+    submanifold rulebook 16 V + 8 R per level; strided 16 Vl + 8 Vl + 16 Vl+1."""
+    import ctypes
+    from mopa_b200 import _lib
+    from mopa_b200.scn import compiler, functional as F
+    prog = compiler.compiled_for(net.sparseModel)
+    L = _lib.load()
+    dev = batches_dev[0][1].device
+    handle = prog.ensure_handle(dev.index)
+    stream = torch.cuda.current_stream(dev).cuda_stream
     ms, bytes_ = [], 0
     for rep in range(reps + 2):
         c, f = batches_dev[rep % len(batches_dev)]
+        m = F.Metadata(3, dev)
+        n_active = (ctypes.c_int64 * prog.n_levels)()
+        sizes = (ctypes.c_uint64 * 3)()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
         e0.record()
-        m = F.Metadata(3, f.device)
-        v = [m.set_locations(c, 4096, 4)]
-        size = 4096
-        for level in range(7):
-            m.prepare_submanifold(size, 3)
-            if level < 6:
-                v.append(m.prepare_convolution(size, size // 2, 2, 2))
-                size //= 2
+        _lib.check(L.mopa_scn_Program_prepare(handle, m._h, c.data_ptr(), c.shape[0], c.shape[1], 1, F._cfg["precision"], stream,
+                                              n_active, sizes))
         e1.record()
         torch.cuda.synchronize()
         if rep >= 2:
             ms.append(e0.elapsed_time(e1))
         if rep == reps + 1:  # rule counts through the inspection call, outside the timed region
-            n = c.shape[0]
-            bytes_ = n * (32 + 4 + 4) + 4 * v[0]
+            v = [int(x) for x in n_active]
+            bytes_ = c.shape[0] * (32 + 4 + 4) + 4 * v[0]
             size = 4096
-            for level in range(7):
+            for level in range(prog.n_levels):
                 bytes_ += 16 * v[level] + 8 * sum(m.submanifold_rule_counts(size))
-                if level < 6:
+                if level + 1 < prog.n_levels:
                     bytes_ += 16 * v[level] + 8 * v[level] + 16 * v[level + 1]
                 size //= 2
         del m
     peak = peaks.get("hbm_gbs", 6650.0)
     med = float(np.median(ms))
     return {"ms_per_forward": med, "algorithmic_bytes": int(bytes_), "achieved_gbs": bytes_ / med / 1e6,
-            "frac": bytes_ / med / 1e6 / peak, "note": "k_insert / k_flag_first / scans / k_subm_table / k_tile_lists ... incl. the "
-            "7 count read-backs (host syncs); in a step this runs on its own stream ahead of the convolutions"}
+            "frac": bytes_ / med / 1e6 / peak,
+            "note": "mopa_scn_Program_prepare: k_insert / k_unique_scan / k_read_ids per level, k_subm_tiles, k_tile_lists, "
+                    "CSR lists; ~45 small launches and one count read-back: launch- and latency-bound, not bandwidth-bound"}
 
 
 def run_ours(a):
@@ -391,7 +397,7 @@ def run_ours(a):
     roof = geo = None
     if rank == 0 and not a.no_roofline:
         roof = roofline_pass(net, dev, min(a.steps, 8), peaks)
-        geo = geometry_pass(dev, peaks)
+        geo = geometry_pass(net, dev, peaks)
     if world > 1:
         dist.barrier()
     cpu = None

@@ -39,7 +39,7 @@ constexpr int kDwTcSub = 512;    // granularity of an item's row range (a multip
 constexpr int kDwTcMaxTiles = 2048;  // rulebook tiles per item (prefix counts in shared memory); caps rows per item
 constexpr int kDwTcList = kDwTcMaxTiles / 2 + 4;  // 8-byte slots of the prefix block (kDwTcMaxTiles + 1 ints)
 constexpr int kDwTcMaxStages = 12;
-constexpr int kDwTcAhead = 3;  // stages between fetching a rule's list entry and copying its rows
+constexpr int kDwTcAhead = 8;  // stages between fetching a rule's list entry and copying its rows
 
 struct DwTcPlan {
     int centre;  // 13 for a submanifold table, -1 otherwise
@@ -243,11 +243,17 @@ __global__ void __launch_bounds__(kDwTcThreads)
         const int n_rules = ntile > 0 ? (int)lds_u32(pre_a + 4 * ntile) : 0;
         const int n_stage = n_rules > 0 ? (n_rules + kDwTcTile - 1) / kDwTcTile : 1;  // an empty item still zeroes its slice
         const int32_t *tl_k = gt.tl + ((t0 * K + k) << 7);
-        int j = 0;  // running tile pointer of this thread
+        // running tile pointer of this thread with the tile's rule range [lo, hi) in registers: the common case (the next
+        // rule is in the same tile) touches no shared memory (a dependent LDS chain per stage cost ~25 % of the kernel)
+        int j = 0, lo = 0, hi = ntile > 0 ? (int)lds_u32(pre_a + 4) : 0;
         auto locate = [&](int g, int &tile) -> int {  // list entry of rule g (g < n_rules)
-            while (g >= (int)lds_u32(pre_a + 4 * (j + 1))) ++j;
+            while (g >= hi) {
+                ++j;
+                lo = hi;
+                hi = (int)lds_u32(pre_a + 4 * (j + 1));
+            }
             tile = j;
-            return __ldg(tl_k + (((int64_t)j * K) << 7) + (g - (int)lds_u32(pre_a + 4 * j)));
+            return __ldg(tl_k + (((int64_t)j * K) << 7) + (g - lo));
         };
         // entries are fetched kDwTcAhead stages before their stage is filled (register ring with static indices): a stage
         // is shorter than an L2 / HBM round trip

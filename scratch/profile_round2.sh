@@ -14,7 +14,7 @@ B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-roofline --no-fp3
 $T 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/${TG}_launches.csv $B > /dev/null 2>&1
 export MOPA_SCN_NO_DW_OVERLAP=1
 $T 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum --clock-control none -k regex:k_conv_tc -c 260 --csv --log-file $O/${TG}_conv_tc_traffic.csv $B > /dev/null 2>&1
-for spec in "k_conv_tc 150 4 conv_tc" "k_dw_tc\$ 78 3 dw_tc" "k_bn_fused 156 3 bn_fused"; do
+for spec in "k_conv_tc 150 4 conv_tc" "k_dw_tc\$ 78 3 dw_tc" "k_bn_stats 100 3 bn_stats"; do
   set -- $spec
   $T 300 ncu --set full --clock-control none --import-source on -k regex:$1 -s $2 -c $3 -o /tmp/${TG}_$4 $B > /dev/null 2>&1
   ncu -i /tmp/${TG}_$4.ncu-rep --page raw --csv > $O/${TG}_$4_raw.csv 2>/dev/null
