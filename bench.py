@@ -282,7 +282,7 @@ def geometry_pass(net, batches_dev, peaks, reps=10):
     med = float(np.median(ms))
     return {"ms_per_forward": med, "algorithmic_bytes": int(bytes_), "achieved_gbs": bytes_ / med / 1e6,
             "frac": bytes_ / med / 1e6 / peak,
-            "note": "mopa_scn_Program_prepare: k_insert / k_unique_scan / k_read_ids per level, k_subm_tiles, k_tile_lists, "
+            "note": "mopa_scn_Program_prepare: k_insert / k_unique_scan / k_read_ids per level, k_subm_tiles_batch, k_tile_lists_batch (all levels per launch), "
                     "CSR lists; ~45 small launches and one count read-back: launch- and latency-bound, not bandwidth-bound"}
 
 

@@ -183,13 +183,18 @@ __global__ void __launch_bounds__(256) k_bn_apply(const float *__restrict__ x, i
     }
 }
 
+// sums != nullptr: the two column sums S1 = sum d, S2 = sum (x - mean) d were reduced by the producing d_input convolution's
+// epilogue (conv_tc.cu); every block derives gradMean / k from them, block 0 also writes the affine gradients: the whole
+// BatchNorm backward is this one streaming kernel.
 template <int VEC>
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float *__restrict__ x, int64_t ld_x,
                                                       const float *__restrict__ dout, int64_t ld_dout,
                                                       float *__restrict__ din, int64_t ld_din, int64_t n, int planes,
                                                       const float *__restrict__ mean, const float *__restrict__ invstd,
                                                       const float *__restrict__ weight, const float *__restrict__ bias,
-                                                      const float *__restrict__ ws, float leakiness, int accumulate) {
+                                                      const float *__restrict__ ws, float leakiness, int accumulate,
+                                                      const double *__restrict__ sums, int train,
+                                                      float *__restrict__ d_weight, float *__restrict__ d_bias, float inv_n) {
     const int c0 = threadIdx.x * VEC;
     float sc[VEC], sh[VEC], mu[VEC], gm[VEC], kk[VEC];
 #pragma unroll
@@ -197,24 +202,41 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float *__restrict__ 
         mu[e] = mean[c0 + e];
         sc[e] = invstd[c0 + e] * weight[c0 + e];
         sh[e] = bias[c0 + e] - mu[e] * sc[e];
-        gm[e] = ws[8 + c0 + e];
-        kk[e] = ws[8 + planes + c0 + e];
+        if (sums) {
+            // (the sums are fp64 because they are accumulated with atomics in any order; their values fit fp32 math)
+            const float a = (float)sums[c0 + e], b = (float)sums[kStatsLd + c0 + e], is = invstd[c0 + e];
+            gm[e] = train ? a * inv_n : 0.f;
+            kk[e] = train ? b * is * is * inv_n : 0.f;
+            if (blockIdx.x == 0 && threadIdx.y == 0) {
+                if (d_weight) d_weight[c0 + e] = b * is;
+                if (d_bias) d_bias[c0 + e] = a;
+            }
+        } else {
+            gm[e] = ws[8 + c0 + e];
+            kk[e] = ws[8 + planes + c0 + e];
+        }
     }
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; r < n; r += (int64_t)gridDim.x * blockDim.y) {
-        float v[VEC], d[VEC];
-        Vec<VEC>::get(x + r * ld_x + c0, v);
-        Vec<VEC>::get(dout + r * ld_dout + c0, d);
+    auto one = [&](float (&v)[VEC], const float (&d)[VEC]) {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             const float y = fmaf(v[e], sc[e], sh[e]);
             const float dm = y > 0.f ? d[e] : d[e] * leakiness;
             v[e] = (dm - gm[e] - (v[e] - mu[e]) * kk[e]) * sc[e];
         }
+    };
+    // (one row per iteration: a thread sees ~6 rows at the largest level; four rows in flight measured 2 us slower per call)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.y;
+    int64_t r = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    for (; r < n; r += stride) {
+        float v[VEC], d[VEC];
+        Vec<VEC>::get(x + r * ld_x + c0, v);
+        Vec<VEC>::get(dout + r * ld_dout + c0, d);
+        one(v, d);
         if (accumulate) {
             float old[VEC];
             Vec<VEC>::get(din + r * ld_din + c0, old);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) v[e] = __fadd_rn(v[e], old[e]);  // no FMA contraction: same bits as a separate add
+            for (int e = 0; e < VEC; ++e) v[e] = __fadd_rn(v[e], old[e]);
         }
         Vec<VEC>::put(din + r * ld_din + c0, v);
     }
@@ -418,17 +440,21 @@ __global__ void __launch_bounds__(256) k_bn_apply_sums(const float *__restrict__
                                                        const float *__restrict__ bias, float leakiness, float eps,
                                                        float momentum, float *__restrict__ save_mean,
                                                        float *__restrict__ save_invstd, float *__restrict__ running_mean,
-                                                       float *__restrict__ running_var) {
+                                                       float *__restrict__ running_var, double inv_n) {
     const int c0 = threadIdx.x * VEC;
     const double dn = (double)n;
     float sc[VEC], sh[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
         const int c = c0 + e;
-        const double mean = sums[c] / dn;
-        double m2 = sums[kStatsLd + c] - mean * mean * dn;  // sum (x - mean)^2
+        // every thread repeats this per-column prologue for a handful of rows: fp64 only where the cancellation needs it
+        // (two multiplies and one FMA), no fp64 division or square root
+        const double mean = sums[c] * inv_n;
+        double m2 = fma(-mean * dn, mean, sums[kStatsLd + c]);  // sum (x - mean)^2
         if (m2 < 0.0) m2 = 0.0;
-        const float invstd = (float)(1.0 / sqrt(m2 / dn + (double)eps));
+        const float var = (float)(m2 * inv_n) + eps;
+        float invstd = rsqrtf(var);
+        invstd = invstd * fmaf(-0.5f * var * invstd, invstd, 1.5f);  // one Newton step: full fp32 accuracy
         sc[e] = invstd * weight[c];
         sh[e] = bias[c] - (float)mean * sc[e];
         if (blockIdx.x == 0 && threadIdx.y == 0) {
@@ -615,7 +641,8 @@ int bn_forward(const float *in, int64_t ld_in, float *out, int64_t ld_out, float
     const int prof = prof_begin(40, nullptr, planes, planes, n_active, s);
     if (train && stats && sh.vec == 4) {  // the producing convolution accumulated the column sums in its epilogue
         k_bn_apply_sums<4><<<sh.grid, sh.block, 0, s>>>(in, ld_in, out, ld_out, n_active, planes, stats, weight, bias, leakiness,
-                                                        eps, momentum, save_mean, save_invstd, running_mean, running_var);
+                                                        eps, momentum, save_mean, save_invstd, running_mean, running_var,
+                                                        1.0 / (double)n_active);
         MOPA_LAUNCHED();
         prof_end(prof, s);
         return 0;
@@ -657,7 +684,7 @@ int bn_forward(const float *in, int64_t ld_in, float *out, int64_t ld_out, float
 int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, const float *d_out, int64_t ld_dout,
                 const float *save_mean, const float *save_invstd, const float *weight, const float *bias, float *d_weight,
                 float *d_bias, float leakiness, int train, int64_t n_active, int planes, void *workspace, int accumulate,
-                cudaStream_t s) {
+                cudaStream_t s, const double *sums) {
     MOPA_CHECK(planes > 0 && planes <= 256, "BatchNormalization: planes must be in [1, 256]");
     if (n_active == 0) {
         if (d_weight) MOPA_CUDA(cudaMemsetAsync(d_weight, 0, (size_t)planes * 4, s));
@@ -669,6 +696,14 @@ int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, con
     MOPA_CHECK(sh.block.x * sh.block.y <= 256, "BatchNormalization: unaligned features with more than 256 planes");
     float *ws = reinterpret_cast<float *>(workspace);
     const int prof = prof_begin(50, nullptr, planes, planes, n_active, s);
+    if (sums && d_in && sh.vec == 4) {  // the producing d_input convolution reduced the column sums in its epilogue
+        k_bn_bwd_apply<4><<<sh.grid, sh.block, 0, s>>>(in, ld_in, d_out, ld_dout, d_in, ld_din, n_active, planes, save_mean,
+                                                       save_invstd, weight, bias, ws, leakiness, accumulate, sums, train,
+                                                       d_weight, d_bias, (float)(1.0 / (double)n_active));
+        MOPA_LAUNCHED();
+        prof_end(prof, s);
+        return 0;
+    }
     if (sh.vec == 4 && bn_fused_enabled() && n_active * planes >= bn_fused_min_elems()) {
         const BnShapeArgs A{in, ld_in, d_out, ld_dout, d_in, ld_din, n_active, planes, ws, save_mean, save_invstd, weight, bias,
                             leakiness, train, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, d_weight, d_bias, accumulate};
@@ -688,10 +723,12 @@ int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, con
     if (d_in) {
         if (sh.vec == 4)
             k_bn_bwd_apply<4><<<sh.grid, sh.block, 0, s>>>(in, ld_in, d_out, ld_dout, d_in, ld_din, n_active, planes,
-                                                           save_mean, save_invstd, weight, bias, ws, leakiness, accumulate);
+                                                           save_mean, save_invstd, weight, bias, ws, leakiness, accumulate,
+                                                           nullptr, train, nullptr, nullptr, 0.f);
         else
             k_bn_bwd_apply<1><<<sh.grid, sh.block, 0, s>>>(in, ld_in, d_out, ld_dout, d_in, ld_din, n_active, planes,
-                                                           save_mean, save_invstd, weight, bias, ws, leakiness, accumulate);
+                                                           save_mean, save_invstd, weight, bias, ws, leakiness, accumulate,
+                                                           nullptr, train, nullptr, nullptr, 0.f);
         MOPA_LAUNCHED();
     }
     prof_end(prof, s);

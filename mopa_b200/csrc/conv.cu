@@ -609,7 +609,7 @@ static int dispatch_np(const Gather &gt, const float *in, int64_t ld_in, float *
 // out (n_out rows, c_out) = gather-conv of in with the (possibly transposed / flipped) weights
 int conv_apply(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *weight,
                const float *packed, int n_in0, int n_out0, int transpose, int flip, int precision, cudaStream_t s,
-               double *stats, bool *stats_done) {
+               double *stats, bool *stats_done, const TcBnBwd *bn) {
     // stats: per-column sum / sum of squares of the output rows are added there IF the tcgen05 kernel runs this op
     // (*stats_done tells the caller); the BatchNorm that follows then skips its own statistics pass
     if (stats_done) *stats_done = false;
@@ -641,7 +641,7 @@ int conv_apply(const Gather &gt, const float *in, int64_t ld_in, float *out, int
     if (!split && conv_tc_enabled() && conv_tc_supported(c_in, c_out))
     {
         if (stats_done) *stats_done = stats != nullptr;
-        return conv_apply_tc(gt, in, ld_in, out, ld_out, packed, c_in, c_out, stats, s);
+        return conv_apply_tc(gt, in, ld_in, out, ld_out, packed, c_in, c_out, stats, s, stats ? bn : nullptr);
     }
     switch (c_out / 16) {
         case 1: return dispatch_np<1>(gt, in, ld_in, out, ld_out, packed, c_in, split, s);

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kDwTcThreads)
             if (++st == stages) { st = 0; ph ^= 1; }
         };
 
-        // The item's rules come straight from the tile rulebook (geometry.cu::k_tile_lists): per tile of 128 output rows a
+        // The item's rules come straight from the tile rulebook (geometry.cu::k_tile_lists_batch): per tile of 128 output rows a
         // compact, row-ordered list of this offset's rules. The producers first put the running rule counts of the item's
         // tiles into shared memory; rule g of the item is then entry g - prefix[j] of tile j, and because a thread's g grows
         // by 32 per stage it finds j with a running pointer. No table lookups, ballots or block barriers per pass.

@@ -13,7 +13,7 @@
 // dense (offset, row) -> row table, the gather warps spend ~130 instructions per (warp, offset) on ballots, shuffles and
 // bookkeeping for ~4 live rows, 16 such warps per SM: the kernel was INSTRUCTION-ISSUE bound (0.21 of the HBM roofline,
 // DRAM 6-8 % busy, tensor pipe 4-14 %). Cutting the LDGSTS count 3-6x by compacting inside the warp changed nothing.
-// So the compaction moved out of this kernel: geometry.cu::k_tile_lists builds, once per level and shared by the six
+// So the compaction moved out of this kernel: geometry.cu::k_tile_lists_batch builds, once per level and shared by the six
 // convolution passes that use the level, the rulebook in the form this kernel consumes: per (tile, offset) a compact
 // list of (input row, tile row) pairs and the 128-bit row mask. Here
 //   warps 0-7  gather : 4 per tile. Live offsets of the CTA are dealt round-robin to the tile's 4 warps; ONE warp
@@ -29,6 +29,9 @@
 // Offsets with no rule in any tile of the CTA are skipped by all three roles (same 27-bit live set, from the masks).
 // Summation order is fixed (live k ascending, chunks ascending, hardware order inside an MMA): outputs are deterministic.
 #include <stdlib.h>
+
+#include <mutex>
+#include <vector>
 
 #include "geometry.cuh"
 #include "mopa_scn.h"
@@ -93,32 +96,64 @@ __device__ long long g_tc_trace[8][512];
 #endif
 
 struct TcSmem {  // byte offsets inside the dynamic shared memory block (base aligned to 1024)
-    int a, b, bars, total;
+    int a, b, bars, cst, total;
 };
-__host__ __device__ inline TcSmem tc_smem_layout(int nt, int sa, int sb, int na = 1) {  // na: 32-channel atoms per stage
+__host__ __device__ inline TcSmem tc_smem_layout(int nt, int sa, int sb, int na = 1, bool bn = false) {  // na: 32-channel atoms per stage
     TcSmem L;
     L.a = 0;
     L.b = L.a + sa * na * kTcAStage;
     L.bars = L.b + sb * na * nt * 128;
-    L.total = L.bars + 8 * (2 * kTcMaxSA + 2 * kTcMaxSB + 1) + 16;
+    L.cst = (L.bars + 8 * (2 * kTcMaxSA + 2 * kTcMaxSB + 1) + 16 + 15) & ~15;  // [scale | shift | mean] of the BatchNorm in front (d_input pass)
+    L.total = L.cst + (bn ? 3 * nt * 4 : 0);
     return L;
 }
 
+// The less common arguments of a launch.
+//  * split > 1: `split` CTAs (blockIdx.y) share one output tile, each takes every split-th live offset. A CTA parks its
+//    partial accumulator in `partial` ([tile][part][column][128 rows], L2-resident), takes a ticket, and the LAST CTA of
+//    the tile to arrive adds the parts in part order (deterministic whatever the arrival order) and runs the epilogue.
+//    For the small levels: 29-72 tiles would leave most SMs idle while each CTA walks 27 offsets one after the other.
+//  * bn_x != nullptr (d_input pass whose output is the gradient of a BatchNormReLU's output): the epilogue also reduces,
+//    per column, S1 = sum d and S2 = sum (x - mean) d with d = the gradient masked by the sign of the recomputed BatchNorm
+//    output, into `stats` -- the BatchNorm backward that follows then needs no reduction pass of its own.
+struct TcExtra {
+    float *partial;
+    unsigned *tickets;
+    int split;
+    const float *bn_x;
+    int64_t ld_bn_x;
+    const float *bn_mean, *bn_invstd, *bn_weight, *bn_bias;
+    float leak;
+    int bn_ring;  // the tile's rows of x are staged through the A ring (32-column slices) instead of read row by row
+};
+
+__device__ __forceinline__ float4 tc_lds128(uint32_t addr) {  // explicit shared-space load (pointers derived from the aligned
+    float4 t;                                                   // dynamic block are generic to the compiler: LD, not LDS)
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr));
+    return t;
+}
+__device__ __forceinline__ void tc_bar_sync_128(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
 // WIDE = 1: up to 17 warps, one CTA per SM; WIDE = 0: up to 13 warps (two tiles x two issuers), two CTAs per SM;
 // WIDE = 2: 11 warps (two tiles, one issuer each), three CTAs per SM (narrow layers: small weight stages)
-template <int NA, int LPR, int WIDE>
+// BN = true: the d_input pass in front of a BatchNorm (TcExtra::bn_x); a separate instantiation, so that the forward
+// kernels do not carry its code: the prologue and the epilogue run once per CTA, from a cold instruction cache.
+template <int NA, int LPR, int WIDE, bool BN>
 __global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 32 : 13 * 32), WIDE == 1 ? 1 : (WIDE == 2 ? 3 : 2))
     k_conv_tc(Gather gt, const float *__restrict__ in, int64_t ld_in, float *__restrict__ out, int64_t ld_out,
               const float *__restrict__ packed, int c_in, int NT, int SA, int SB, int TPC, int GW, int ACC,
-              double *__restrict__ stats) {
+              double *__restrict__ stats, const __grid_constant__ TcExtra X) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    const TcSmem L = tc_smem_layout(NT, SA, SB, NA);
+    const TcSmem L = tc_smem_layout(NT, SA, SB, NA, BN);
     unsigned char *sA = smem + L.a, *sB = smem + L.b;
     uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + L.bars), *a_empty = a_full + kTcMaxSA;
     uint64_t *b_full = a_empty + kTcMaxSA, *b_empty = b_full + kTcMaxSB;
     uint64_t *d_full = b_empty + kTcMaxSB;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(d_full + 1);
+    volatile int *final_flag = reinterpret_cast<volatile int *>(tmem_ptr + 1);  // split launches: this CTA runs the epilogue
+    float *cst = reinterpret_cast<float *>(smem + L.cst);
+    const int S = X.split;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2, 7, 0);
@@ -144,7 +179,21 @@ __global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 
         mk0 = __ldg(gt.tm + tile0 * K + lane);
         if (n_mt == 2) mk1 = __ldg(gt.tm + (tile0 + 1) * K + lane);
     }
-    const uint32_t liveset = __ballot_sync(0xffffffffu, (mk0.x | mk0.y | mk0.z | mk0.w | mk1.x | mk1.y | mk1.z | mk1.w) != 0u);
+    uint32_t liveset = __ballot_sync(0xffffffffu, (mk0.x | mk0.y | mk0.z | mk0.w | mk1.x | mk1.y | mk1.z | mk1.w) != 0u);
+    if (S > 1) {  // this CTA's share: live offsets number blockIdx.y, blockIdx.y + S, ...
+        uint32_t mine = 0;
+        int r = 0;
+        for (uint32_t rest = liveset; rest; rest &= rest - 1, ++r)
+            if (r % S == (int)blockIdx.y) mine |= rest & (0u - rest);
+        liveset = mine;
+    }
+    if (BN && tid < NT) {
+        const float mu = X.bn_mean[tid], sc = X.bn_invstd[tid] * X.bn_weight[tid];
+        cst[tid] = sc;
+        cst[NT + tid] = X.bn_bias[tid] - mu * sc;
+        cst[2 * NT + tid] = mu;
+    }
+    if (tid == 0) *final_flag = 1;
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -253,6 +302,31 @@ __global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 
           }
         }
 
+        // d_input pass in front of a BatchNorm: the tile's 128 rows of that BatchNorm's input x follow the gathered stages
+        // through the ring as extra stage-steps, one per 32-column slice and in the same swizzled row layout (fully
+        // coalesced copies that land while the last MMAs drain; the issuers never see them). Slice j is copied by group
+        // j mod GW into the stage its next stage-step would use, so the stage / parity bookkeeping above carries on.
+        const int nslice = (NT + kTcChunk - 1) / kTcChunk;
+        if (BN && X.bn_ring > 0 && live) {
+            const char *xsrc = reinterpret_cast<const char *>(X.bn_x + (row0 + 128 * mt) * X.ld_bn_x);
+            const uint32_t xldb = (uint32_t)X.ld_bn_x * 4;
+            const int rows_here = (int)min((int64_t)128, gt.n_out - (row0 + 128 * mt));
+            for (int j = gi; j < nslice; j += GW) {
+                mbar_wait_s(empty0_a + 8 * st, ph);
+                const uint32_t tile_a = sA_a + st * a_stage;
+                for (int it = mi; it < 32; it += CW) {
+                    const int pidx = it * 32 + lane, r = pidx >> 3, pc = pidx & 7;
+                    const bool ok = r < rows_here && kTcChunk * j + 4 * pc < NT;
+                    cp_async16_guard_s(tile_a + (uint32_t)r * 128u + (uint32_t)((pc ^ (r & 7)) << 4),
+                                       xsrc + (uint64_t)r * xldb + (uint32_t)(128 * j + 16 * pc), ok ? 1u : 0u);
+                }
+                st += TPC * GW;
+                if (st >= SA) { st -= SA; ph ^= 1; }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            named_barrier_sync(2 + mt, 128);  // the tile's four warps: every slice is in shared memory
+        }
+
         // ================================================================= epilogue: TMEM -> HBM, one output row per thread
         TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2, 7, 2);
         if (live) {
@@ -261,54 +335,143 @@ __global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 
             mbar_wait(d_full, 0);
             tc_fence_after_sync();
             TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2, 7, 3);
-            float *dst = out + row * ld_out;
-            float *s_part = reinterpret_cast<float *>(sA) + (size_t)warp * 2 * NT;  // the stage ring is idle by now
-            for (int q = 0; q < NT / 16; ++q) {
-                float v[16];
+            auto load_acc = [&](int q, float (&v)[16]) {  // columns [16 q, +16) of this thread's row, the ACC sets in order
                 tmem_ld16(taddr + 16 * q, v);  // warp-collective: every lane takes part, also beyond n_out
-                for (int ai = 1; ai < ACC; ++ai) {  // the accumulator sets of the tile's other issuers, in order
+#pragma unroll 1
+                for (int ai = 1; ai < ACC; ++ai) {
                     float u[16];
                     tmem_ld16(taddr + (uint32_t)(ai * TPC * NT) + 16 * q, u);
 #pragma unroll
                     for (int e = 0; e < 16; ++e) v[e] += u[e];
                 }
+            };
+            bool run = true;
+            const float *parts = nullptr;
+            if (S > 1) {  // (split launches have one tile per CTA: mt = 0, warps 0-3)
+                float *mine = X.partial + ((size_t)(tile0 * S + blockIdx.y) * NT) * 128 + 32 * wq + lane;
+#pragma unroll 1
+                for (int q = 0; q < NT / 16; ++q) {
+                    float v[16];
+                    load_acc(q, v);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) __stcg(mine + (size_t)(16 * q + e) * 128, v[e]);
+                }
+                __threadfence();
+                tc_bar_sync_128(1);
+                if (warp == 0 && lane == 0) {
+                    const unsigned t = atomicAdd(X.tickets + tile0, 1u);
+                    const int last = t == (unsigned)(S - 1);
+                    if (last) X.tickets[tile0] = 0;  // nobody else touches it any more: ready for the next launch
+                    *final_flag = last;
+                }
+                tc_bar_sync_128(1);
+                run = *final_flag != 0;
+                if (run) {
+                    __threadfence();
+                    parts = X.partial + ((size_t)tile0 * S * NT) * 128 + 32 * wq + lane;
+                }
+            }
+            float *dst = out + row * ld_out;
+            float *s_part = reinterpret_cast<float *>(sB) + (size_t)warp * 2 * NT;  // the weight ring is idle by now (>= 256 NT bytes)
+#pragma unroll 1
+            for (int q = 0; run && q < NT / 16; ++q) {
+                float v[16];
+                if (S > 1) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = __ldcg(parts + (size_t)(16 * q + e) * 128);
+#pragma unroll 1
+                    for (int part = 1; part < S; ++part) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] += __ldcg(parts + ((size_t)part * NT + 16 * q + e) * 128);
+                    }
+                } else {
+                    load_acc(q, v);
+                }
+                TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2 && q == 0, 7, 6);
                 if (row < gt.n_out) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         float4 o = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
                         float4 *p = reinterpret_cast<float4 *>(dst + 16 * q + 4 * e);
-                        if (gt.accumulate) { const float4 x = *p; o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w; }
+                        if (gt.accumulate) {
+                            const float4 x = *p;
+                            o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+                            v[4 * e] = o.x; v[4 * e + 1] = o.y; v[4 * e + 2] = o.z; v[4 * e + 3] = o.w;
+                        }
                         *p = o;
                     }
                 }
-                if (stats) {  // warp-uniform: per-column sum / sum of squares for the BatchNorm that follows
-                    float a[16], b[16];
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        a[e] = row < gt.n_out ? v[e] : 0.f;
-                        b[e] = a[e] * a[e];
+                TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2 && q == 0, 7, 7);
+                if (stats) {  // warp-uniform: two per-column sums for the BatchNorm next to this convolution
+                    // Eight columns at a time (register budget: 56 per thread at three CTAs per SM; sixteen at a time spilled
+                    // ~70 bytes per thread into the epilogue's dependency chain).
+                    const bool in_range = row < gt.n_out;
+                    uint32_t x_a = 0;  // ring mode: shared address of this thread's row in the slice that holds columns 16 q ..
+                    if (BN && X.bn_ring > 0) {
+                        // slice j = q / 2 went into the stage of step n_j: the first step index >= G congruent to
+                        // j mod GW, plus GW (j / GW), G = the stage-steps of the main loop
+                        const int G = __popc(liveset) * nchunk, j = q >> 1, g = j % GW;
+                        const int nj = G + ((g - G) % GW + GW) % GW + GW * (j / GW);
+                        x_a = sA_a + (uint32_t)((mt + TPC * nj) % SA) * a_stage + (uint32_t)(32 * wq + lane) * 128u;
                     }
-                    // butterfly: after strides 16, 8, 4, 2 a lane holds ONE column's sum over 16 of the 32 rows
-                    // (column = bits 4..1 of the lane, msb first); stride 1 adds the two halves
+                    const uint32_t c_a = smem_u32(cst) + 64u * (uint32_t)q;
 #pragma unroll
-                    for (int w = 8, stride = 16; w >= 1; w >>= 1, stride >>= 1) {
-                        const bool up = lane & stride;
+                    for (int h = 0; h < 2; ++h) {
+                        float a[8], b[8];
+                        if (BN) {  // d_input pass: S1 = sum d, S2 = sum (x - mean) d, d = gradient through the ReLU
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            if (e < w) {
-                                const float sa = up ? a[e] : a[e + w], ka = up ? a[e + w] : a[e];
-                                const float sb2 = up ? b[e] : b[e + w], kb = up ? b[e + w] : b[e];
-                                a[e] = ka + __shfl_xor_sync(0xffffffffu, sa, stride);
-                                b[e] = kb + __shfl_xor_sync(0xffffffffu, sb2, stride);
+                            for (int e4 = 0; e4 < 2; ++e4) {
+                                const int p4 = 2 * h + e4;  // 16-byte piece of this thread's 64-byte row segment
+                                float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (X.bn_ring > 0) x4 = tc_lds128(x_a + (uint32_t)((((q & 1) * 4 + p4) ^ (lane & 7)) << 4));
+                                else if (in_range) x4 = __ldg(reinterpret_cast<const float4 *>(X.bn_x + row * X.ld_bn_x + 16 * q) + p4);
+                                const float4 sc4 = tc_lds128(c_a + 16 * p4), sh4 = tc_lds128(c_a + 4 * NT + 16 * p4),
+                                             mu4 = tc_lds128(c_a + 8 * NT + 16 * p4);
+                                const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w},
+                                            sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w}, mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float x = in_range ? xs[i] : 0.f;  // (rows past the end: whatever the stage holds)
+                                    const float y = fmaf(x, sc[i], sh[i]);
+                                    const float g = v[8 * h + 4 * e4 + i];
+                                    const float d = in_range ? (y > 0.f ? g : g * X.leak) : 0.f;
+                                    a[4 * e4 + i] = d;
+                                    b[4 * e4 + i] = (x - mu[i]) * d;
+                                }
+                            }
+                        } else {  // forward: sum x, sum x^2 of the rows just written
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                a[e] = in_range ? v[8 * h + e] : 0.f;
+                                b[e] = a[e] * a[e];
                             }
                         }
-                    }
-                    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-                    b[0] += __shfl_xor_sync(0xffffffffu, b[0], 1);
-                    if (!(lane & 1)) {
-                        const int col = 16 * q + (((lane >> 4) & 1) << 3) + (((lane >> 3) & 1) << 2) + (((lane >> 2) & 1) << 1) + ((lane >> 1) & 1);
-                        s_part[col] = a[0];
-                        s_part[NT + col] = b[0];
+                        TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2 && q == 0, 7, 8 + 2 * h);
+                        // butterfly: after strides 16, 8, 4 a lane holds ONE column's sum over 8 of the 32 rows (column =
+                        // bits 4..2 of the lane, msb first); strides 2 and 1 add the four quarters
+#pragma unroll
+                        for (int w = 4, stride = 16; w >= 1; w >>= 1, stride >>= 1) {
+                            const bool up = lane & stride;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                if (e < w) {
+                                    const float sa = up ? a[e] : a[e + w], ka = up ? a[e + w] : a[e];
+                                    const float sb2 = up ? b[e] : b[e + w], kb = up ? b[e + w] : b[e];
+                                    a[e] = ka + __shfl_xor_sync(0xffffffffu, sa, stride);
+                                    b[e] = kb + __shfl_xor_sync(0xffffffffu, sb2, stride);
+                                }
+                            }
+                        }
+                        a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
+                        b[0] += __shfl_xor_sync(0xffffffffu, b[0], 2);
+                        a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+                        b[0] += __shfl_xor_sync(0xffffffffu, b[0], 1);
+                        TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2 && q == 0, 7, 9 + 2 * h);
+                        if (!(lane & 3)) {
+                            const int col = 16 * q + 8 * h + (((lane >> 4) & 1) << 2) + (((lane >> 3) & 1) << 1) + ((lane >> 2) & 1);
+                            s_part[col] = a[0];
+                            s_part[NT + col] = b[0];
+                        }
                     }
                 }
             }
@@ -396,11 +559,13 @@ __global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 
     __syncthreads();
     TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2, 7, 5);
     if (warp == 9) tmem_dealloc(tmem_base, tmem_cols);
-    if (stats && tid < 2 * NT) {  // [0, NT): sum x, [NT, 2 NT): sum x^2; warps of the tiles that hold rows, in order
-        const float *s_all = reinterpret_cast<const float *>(sA);
-        float sum = 0.f;
-        for (int w = 0; w < 4 * n_mt; ++w) sum += s_all[(size_t)w * 2 * NT + tid];
-        atomicAdd(stats + (tid < NT ? tid : kTcStatsLd + (tid - NT)), (double)sum);
+    if (stats && *final_flag) {  // [0, NT): first sum, [NT, 2 NT): second; warps of the tiles that hold rows, in order
+        const float *s_all = reinterpret_cast<const float *>(sB);
+        for (int i = tid; i < 2 * NT; i += (int)blockDim.x) {  // (2 NT = 384 on the widest d_input pass, 352 threads)
+            float sum = 0.f;
+            for (int w = 0; w < 4 * n_mt; ++w) sum += s_all[(size_t)w * 2 * NT + i];
+            atomicAdd(stats + (i < NT ? i : kTcStatsLd + (i - NT)), (double)sum);
+        }
     }
 }
 
@@ -447,10 +612,52 @@ static int env_int(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
+// Parking space of the split launches: [1024 tickets | partial accumulators], one block per (device, stream), grown on
+// demand with the stream-ordered allocator (the old block is freed behind the kernels that may still use it).
+constexpr int kTcSplitMaxTiles = 1024;
+static int split_workspace(size_t partial_bytes, cudaStream_t s, float **partial, unsigned **tickets) {
+    struct Block { int device; cudaStream_t stream; char *p; size_t bytes; };
+    static std::mutex mu;
+    static std::vector<Block> blocks;
+    int dev = 0;
+    MOPA_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    Block *b = nullptr;
+    for (Block &x : blocks)
+        if (x.device == dev && x.stream == s) b = &x;
+    if (!b) { blocks.push_back(Block{dev, s, nullptr, 0}); b = &blocks.back(); }
+    const size_t need = (size_t)kTcSplitMaxTiles * 4 + partial_bytes;
+    if (b->bytes < need) {
+        size_t want = (size_t)32 << 20;
+        while (want < need) want <<= 1;
+        char *fresh = nullptr;
+        MOPA_CUDA(cudaMallocAsync((void **)&fresh, want, s));
+        MOPA_CUDA(cudaMemsetAsync(fresh, 0, (size_t)kTcSplitMaxTiles * 4, s));
+        if (b->p) MOPA_CUDA(cudaFreeAsync(b->p, s));
+        b->p = fresh;
+        b->bytes = want;
+    }
+    *tickets = reinterpret_cast<unsigned *>(b->p);
+    *partial = reinterpret_cast<float *>(b->p + (size_t)kTcSplitMaxTiles * 4);
+    return 0;
+}
+
+template <bool BN>
+static int tc_configure() {
+#define MOPA_TC_ATTR(NA_, LPR_, W_) \
+    MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<NA_, LPR_, W_, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+    MOPA_TC_ATTR(1, 4, 0); MOPA_TC_ATTR(1, 8, 0); MOPA_TC_ATTR(2, 8, 0);
+    MOPA_TC_ATTR(1, 4, 1); MOPA_TC_ATTR(1, 8, 1); MOPA_TC_ATTR(2, 8, 1);
+    MOPA_TC_ATTR(1, 4, 2); MOPA_TC_ATTR(1, 8, 2);
+#undef MOPA_TC_ATTR
+    return 0;
+}
+
 int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *packed,
-                  int c_in, int c_out, double *stats, cudaStream_t s) {
+                  int c_in, int c_out, double *stats, cudaStream_t s, const TcBnBwd *bn) {
     const int nt = c_out;
     MOPA_CHECK(gt.tl && gt.tm, "conv_tc: the gather has no tile rulebook");
+    MOPA_CHECK(!bn || stats, "conv_tc: BatchNorm-backward sums requested without a statistics block");
     // Shape of the CTA (all overridable for sweeps: MOPA_TC_{CTAS,TPC,SA,SB,NA,ACC}):
     //   tpc  tiles (128 output rows) per CTA: 2 on the large levels (the weight tiles are streamed per CTA), 1 where
     //        256-row CTAs would leave SMs empty
@@ -465,8 +672,10 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
     const int na = want_na ? want_na : ((tpc == 1 && c_in >= 64 && ceil_div(gt.n_out, 128) <= sms) ? 2 : 1);
     bool two = want_ctas >= 2 && (nt <= 64 || tpc == 1) && ceil_div(gt.n_out, 128 * tpc) > sms;  // two CTAs per SM
     // three CTAs per SM (MOPA_TC_CTAS=3): narrow layers of the large levels, two stages per tile, one issuer per tile
+    static const int bn_no3 = env_int("MOPA_TC_BN_NO3", 0);  // A/B: no three-CTA shape for launches that carry BatchNorm sums
     const bool three = want_ctas >= 3 && two && tpc == 2 && na == 1 && nt <= 32 && ceil_div(gt.n_out, 256) > 2 * sms &&
-                       (size_t)tc_smem_layout(nt, 4, 2, 1).total + 1024 <= (size_t)75 * 1024;
+                       !(bn && bn_no3) &&
+                       (size_t)tc_smem_layout(nt, 4, 2, 1, bn != nullptr).total + 1024 <= (size_t)75 * 1024;
     int acc = 1, sb = 2, sa = 0;
     size_t cap = 0;
     for (;;) {
@@ -480,25 +689,18 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
         const int unit = tpc * acc;  // sa must be a multiple of it
         sa = want_sa >= unit && want_sa <= kTcMaxSA ? want_sa : kTcMaxSA;
         sa -= sa % unit;
-        while (sa > unit && (size_t)tc_smem_layout(nt, sa, sb, na).total + 1024 > cap) sa -= unit;
-        const bool fits = (size_t)tc_smem_layout(nt, sa, sb, na).total + 1024 <= cap && tc_tmem_cols(nt, tpc * acc) <= (two ? 256 : 512);
+        while (sa > unit && (size_t)tc_smem_layout(nt, sa, sb, na, bn != nullptr).total + 1024 > cap) sa -= unit;
+        const bool fits = (size_t)tc_smem_layout(nt, sa, sb, na, bn != nullptr).total + 1024 <= cap && tc_tmem_cols(nt, tpc * acc) <= (two ? 256 : 512);
         if (fits && (!two || sa >= 2 * tpc)) break;
         if (two) { two = false; continue; }  // too little room at two CTAs per SM: take the whole SM
         MOPA_CHECK(fits, "conv_tc: shared memory / TMEM layout does not fit");
         break;
     }
-    const size_t smem = (size_t)tc_smem_layout(nt, sa, sb, na).total + 1024;
+    const size_t smem = (size_t)tc_smem_layout(nt, sa, sb, na, bn != nullptr).total + 1024;
     static std::atomic<uint64_t> configured{0};
     MOPA_TRY(once_per_device(configured, [] {
-        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<2, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<2, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MOPA_CUDA(cudaFuncSetAttribute(k_conv_tc<1, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        return 0;
+        MOPA_TRY((tc_configure<false>()));
+        return tc_configure<true>();
     }));
     const int sx = sa / tpc;
     static const int want_gw = env_int("MOPA_TC_GW", 2);  // gather groups per tile (1: all four warps share every stage-step)
@@ -507,27 +709,50 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
     const unsigned threads = 32u * (unsigned)(9 + tpc * acc);
     dim3 grid((unsigned)ceil_div(gt.n_out, 128 * tpc));
     const bool wide = threads > 13 * 32;
-    if (three) {  // 11 warps, <= 75 KB: three CTAs per SM
-        if (c_in == 16)
-            k_conv_tc<1, 4, 2><<<grid, threads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc, gw, acc, stats);
-        else
-            k_conv_tc<1, 8, 2><<<grid, threads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc, gw, acc, stats);
-        MOPA_LAUNCHED();
-        return 0;
+    TcExtra X{};
+    X.split = 1;
+    if (bn) {
+        X.bn_x = bn->x; X.ld_bn_x = bn->ld_x; X.bn_mean = bn->mean; X.bn_invstd = bn->invstd; X.bn_weight = bn->weight;
+        X.bn_bias = bn->bias; X.leak = bn->leak;
+        static const int want_ring = env_int("MOPA_TC_BN_RING", 1);
+        X.bn_ring = want_ring > 0 && ceil_div(nt, kTcChunk) + gw - 1 <= sx;
+        if (want_ring < 0) X.bn_ring = -1;  // A/B: row-by-row loads, no L2 prefetch either
     }
-#define MOPA_TC_LAUNCH(NA_, LPR_)                                                                                         \
-    do {                                                                                                                  \
-        if (wide)                                                                                                         \
-            k_conv_tc<NA_, LPR_, 1><<<grid, threads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc, \
-                                                                gw, acc, stats);                                          \
-        else                                                                                                              \
-            k_conv_tc<NA_, LPR_, 0><<<grid, threads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb, tpc, \
-                                                                gw, acc, stats);                                          \
+    // offsets split over several CTAs per tile where the tiles alone cannot fill the SMs (MOPA_TC_SPLIT=0 disables,
+    // n > 1 forces n parts): as many parts as fit in one wave, at least ~3 live offsets each
+    static const int want_split = env_int("MOPA_TC_SPLIT", -1);
+    if (want_split != 0 && tpc == 1 && !two && (int)grid.x <= kTcSplitMaxTiles) {
+        int parts = want_split > 0 ? want_split : sms / (int)grid.x;
+        if (parts > gt.volume / 3) parts = gt.volume / 3;
+        if (parts > 1) {
+            MOPA_TRY(split_workspace((size_t)grid.x * parts * nt * 128 * 4, s, &X.partial, &X.tickets));
+            X.split = parts;
+            grid.y = (unsigned)parts;
+        }
+    }
+    const bool bnk = X.bn_x != nullptr;
+#define MOPA_TC_GO(NA_, LPR_, W_)                                                                                              \
+    do {                                                                                                                       \
+        if (bnk)                                                                                                               \
+            k_conv_tc<NA_, LPR_, W_, true><<<grid, threads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb,   \
+                                                                       tpc, gw, acc, stats, X);                                \
+        else                                                                                                                   \
+            k_conv_tc<NA_, LPR_, W_, false><<<grid, threads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb,  \
+                                                                        tpc, gw, acc, stats, X);                               \
     } while (0)
-    if (na == 2) MOPA_TC_LAUNCH(2, 8);
-    else if (c_in == 16) MOPA_TC_LAUNCH(1, 4);
+#define MOPA_TC_LAUNCH(NA_, LPR_)               \
+    do {                                        \
+        if (three) MOPA_TC_GO(NA_, LPR_, 2);    \
+        else if (wide) MOPA_TC_GO(NA_, LPR_, 1); \
+        else MOPA_TC_GO(NA_, LPR_, 0);          \
+    } while (0)
+    if (na == 2) {  // (never together with `three`)
+        if (wide) MOPA_TC_GO(2, 8, 1);
+        else MOPA_TC_GO(2, 8, 0);
+    } else if (c_in == 16) MOPA_TC_LAUNCH(1, 4);
     else MOPA_TC_LAUNCH(1, 8);
 #undef MOPA_TC_LAUNCH
+#undef MOPA_TC_GO
     MOPA_LAUNCHED();
     return 0;
 }

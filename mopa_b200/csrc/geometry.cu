@@ -369,68 +369,90 @@ __global__ void __launch_bounds__(256) k_csr_order(const int32_t *__restrict__ p
     rows[beg + r] = (int32_t)i;
 }
 
-// ------------------------------------------------------------------------------------------------ strided links
-__global__ void __launch_bounds__(256) k_child_scatter(const int32_t *__restrict__ parent,
-                                                       const int32_t *__restrict__ kidx, int64_t Vf,
-                                                       int32_t *__restrict__ child, int64_t ld) {
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= Vf) return;
-    child[(int64_t)kidx[c] * ld + parent[c]] = (int32_t)c;
+// ------------------------------------------------------------------------------------------------ strided links, tile rulebooks
+// Each kernel serves SEVERAL levels / links in one launch. After the single host round trip of the voxel pyramid every
+// level's structures are independent of each other: one launch each for all child tables, all strided tile rulebooks and
+// all submanifold levels instead of ~30 small ones (the small levels alone cannot fill the SMs, and a launch costs more
+// than their work). Blocks are numbered through the jobs; first[j] = first block of job j.
+//   k_tile_lists_batch: block = (tile of 128 output rows, offset k): thread r looks up the input row of (k, row 128 t + r)
+//     in the dense table (or the select pair), the block compacts the hits in row order (ballot + popc ranks) and writes
+//     the row mask: the warp-cooperative rulebook build the conv kernels consume (they never ballot / compact).
+//   k_subm_tiles_batch: the same for a submanifold level, fused with the hash probes: thread r probes the grid for the
+//     neighbour of site 128 t + r at offset k and also writes the dense table entry (fp32-mode / small-channel kernels).
+constexpr int kGeoMaxJobs = 16;
+struct GeoJobs {
+    int n;
+    int first[kGeoMaxJobs + 1];
+    int K[kGeoMaxJobs];
+    int64_t V[kGeoMaxJobs], ld[kGeoMaxJobs];
+    const int32_t *table[kGeoMaxJobs], *parent[kGeoMaxJobs], *kidx[kGeoMaxJobs];
+    int32_t *out[kGeoMaxJobs];  // child table (scatter) or tile lists
+    uint4 *tm[kGeoMaxJobs];
+    // submanifold jobs
+    const uint64_t *keys[kGeoMaxJobs], *tab_keys[kGeoMaxJobs];
+    const int32_t *tab_vals[kGeoMaxJobs];
+    int32_t *nbr[kGeoMaxJobs];
+    uint32_t mask[kGeoMaxJobs];
+    int spatial[kGeoMaxJobs];
+};
+__device__ __forceinline__ int geo_job_of(const GeoJobs &J, int block) {
+    int j = 0;
+    while (j + 1 < J.n && block >= J.first[j + 1]) ++j;
+    return j;
 }
-
-// ------------------------------------------------------------------------------------------------ tile rulebooks
-// grid (tiles of 128 output rows, K), 128 threads: thread r looks up the input row of (offset k, output row 128 t + r) in
-// the dense table (or the select pair), the block compacts the hits in row order (ballot + popc ranks) and writes
-// the row mask. This is the warp-cooperative rulebook build the conv kernels consume: they never ballot / compact.
-__global__ void __launch_bounds__(128) k_tile_lists(const int32_t *__restrict__ table, int64_t ld,
-                                                    const int32_t *__restrict__ parent, const int32_t *__restrict__ kidx,
-                                                    int64_t V, int K, int32_t *__restrict__ tl, uint4 *__restrict__ tm) {
+__global__ void __launch_bounds__(256) k_child_scatter_batch(const __grid_constant__ GeoJobs J) {
+    const int j = geo_job_of(J, blockIdx.x);
+    const int64_t c = (int64_t)(blockIdx.x - J.first[j]) * blockDim.x + threadIdx.x;
+    if (c >= J.V[j]) return;
+    J.out[j][(int64_t)J.kidx[j][c] * J.ld[j] + J.parent[j][c]] = (int32_t)c;
+}
+__global__ void __launch_bounds__(128) k_tile_lists_batch(const __grid_constant__ GeoJobs J) {
     __shared__ uint32_t wm[4];
-    const int r = threadIdx.x, lane = r & 31, warp = r >> 5, k = blockIdx.y;
-    const int64_t t = blockIdx.x, o = t * kTileRows + r;
+    const int j = geo_job_of(J, blockIdx.x);
+    const int K = J.K[j], local = blockIdx.x - J.first[j];
+    const int r = threadIdx.x, lane = r & 31, warp = r >> 5, k = local % K;
+    const int64_t t = local / K, o = t * kTileRows + r;
+    const int32_t *table = J.table[j];
     int id = -1;
-    if (o < V) id = table ? __ldg(table + (int64_t)k * ld + o) : (__ldg(kidx + o) == k ? __ldg(parent + o) : -1);
+    if (o < J.V[j]) id = table ? __ldg(table + (int64_t)k * J.ld[j] + o) : (__ldg(J.kidx[j] + o) == k ? __ldg(J.parent[j] + o) : -1);
     const uint32_t m = __ballot_sync(0xffffffffu, id >= 0);
     if (lane == 0) wm[warp] = m;
     __syncthreads();
     int rank = __popc(m & ((1u << lane) - 1u));
     for (int w = 0; w < warp; ++w) rank += __popc(wm[w]);
     const int64_t slot = t * K + k;
-    if (id >= 0) tl[(slot << 7) + rank] = id | (r << kTileRowShift);
-    if (r == 0) tm[slot] = make_uint4(wm[0], wm[1], wm[2], wm[3]);
+    if (id >= 0) J.out[j][(slot << 7) + rank] = id | (r << kTileRowShift);
+    if (r == 0) J.tm[j][slot] = make_uint4(wm[0], wm[1], wm[2], wm[3]);
 }
-
-// Submanifold level in ONE kernel: grid (tiles of 128 sites, 27), 128 threads: thread r probes the hash grid for the
-// neighbour of site 128 t + r at offset k, writes the dense table entry (the fp32-mode and small-channel kernels read it)
-// and the block compacts the hits into the tile rulebook, as k_tile_lists does from a finished table.
-__global__ void __launch_bounds__(128) k_subm_tiles(const uint64_t *__restrict__ keys, int64_t V, int spatial,
-                                                    const uint64_t *__restrict__ tab_keys, const int32_t *__restrict__ tab_vals,
-                                                    uint32_t mask, int32_t *__restrict__ nbr, int64_t ld,
-                                                    int32_t *__restrict__ tl, uint4 *__restrict__ tm) {
+__global__ void __launch_bounds__(128) k_subm_tiles_batch(const __grid_constant__ GeoJobs J) {
     __shared__ uint32_t wm[4];
-    const int r = threadIdx.x, lane = r & 31, warp = r >> 5, k = blockIdx.y;
-    const int64_t t = blockIdx.x, o = t * kTileRows + r;
+    const int j = geo_job_of(J, blockIdx.x);
+    const int local = blockIdx.x - J.first[j];
+    const int r = threadIdx.x, lane = r & 31, warp = r >> 5, k = local % 27;
+    const int64_t t = local / 27, o = t * kTileRows + r;
     int id = -1;
-    if (o < V) {
+    if (o < J.V[j]) {
         if (k == 13) {
             id = (int)o;
         } else {
-            const int dx = k / 9 - 1, dy = (k / 3) % 3 - 1, dz = k % 3 - 1;
+            const int dx = k / 9 - 1, dy = (k / 3) % 3 - 1, dz = k % 3 - 1, spatial = J.spatial[j];
             int x, y, z, b;
-            unpack_key(keys[o], x, y, z, b);
+            unpack_key(J.keys[j][o], x, y, z, b);
             x += dx; y += dy; z += dz;
             if (x >= 0 && y >= 0 && z >= 0 && x < spatial && y < spatial && z < spatial) {
                 const uint64_t q = pack_key((uint32_t)x, (uint32_t)y, (uint32_t)z, (uint32_t)b);
+                const uint64_t *tab_keys = J.tab_keys[j];
+                const uint32_t mask = J.mask[j];
                 uint32_t s = hash_key(q) & mask;
                 while (true) {
                     const uint64_t cur = __ldg(tab_keys + s);
-                    if (cur == q) { id = __ldg(tab_vals + s); break; }
+                    if (cur == q) { id = __ldg(J.tab_vals[j] + s); break; }
                     if (cur == kEmptyKey) break;
                     s = (s + 1) & mask;
                 }
             }
         }
-        nbr[(int64_t)k * ld + o] = id;
+        J.nbr[j][(int64_t)k * J.ld[j] + o] = id;
     }
     const uint32_t m = __ballot_sync(0xffffffffu, id >= 0);
     if (lane == 0) wm[warp] = m;
@@ -438,19 +460,29 @@ __global__ void __launch_bounds__(128) k_subm_tiles(const uint64_t *__restrict__
     int rank = __popc(m & ((1u << lane) - 1u));
     for (int w = 0; w < warp; ++w) rank += __popc(wm[w]);
     const int64_t slot = t * 27 + k;
-    if (id >= 0) tl[(slot << 7) + rank] = id | (r << kTileRowShift);
-    if (r == 0) tm[slot] = make_uint4(wm[0], wm[1], wm[2], wm[3]);
+    if (id >= 0) J.out[j][(slot << 7) + rank] = id | (r << kTileRowShift);
+    if (r == 0) J.tm[j][slot] = make_uint4(wm[0], wm[1], wm[2], wm[3]);
 }
 
-static int build_tile_lists(mopa_scn_metadata *m, const int32_t *table, int64_t ld, const int32_t *parent,
-                            const int32_t *kidx, int64_t V, int64_t n_in, int K, int32_t **tl, uint4 **tm, cudaStream_t s) {
+// allocates the tile rulebook of one (rows, K) and appends the job; the launch follows in flush_tile_jobs
+static int add_tile_job(mopa_scn_metadata *m, GeoJobs &J, const int32_t *table, int64_t ld, const int32_t *parent,
+                        const int32_t *kidx, int64_t V, int64_t n_in, int K, int32_t **tl, uint4 **tm, cudaStream_t s) {
     MOPA_CHECK(n_in < ((int64_t)1 << kTileRowShift), "more than 2^25 active sites at one level: tile rulebook entries overflow");
+    MOPA_CHECK(J.n < kGeoMaxJobs, "too many tile rulebook jobs in one batch");
     const int64_t tiles = ceil_div(V > 0 ? V : 1, kTileRows);
     MOPA_TRY(meta_alloc(m, (void **)tl, (size_t)tiles * K * kTileRows * 4, s));
     MOPA_TRY(meta_alloc(m, (void **)tm, (size_t)tiles * K * sizeof(uint4), s));
-    dim3 grid((unsigned)tiles, (unsigned)K);
-    k_tile_lists<<<grid, 128, 0, s>>>(table, ld, parent, kidx, V, K, *tl, *tm);
+    const int j = J.n++;
+    J.table[j] = table; J.ld[j] = ld; J.parent[j] = parent; J.kidx[j] = kidx; J.V[j] = V; J.K[j] = K;
+    J.out[j] = *tl; J.tm[j] = *tm;
+    J.first[j + 1] = J.first[j] + (int)(tiles * K);
+    return 0;
+}
+static int flush_tile_jobs(GeoJobs &J, cudaStream_t s) {
+    if (J.n == 0) return 0;
+    k_tile_lists_batch<<<(unsigned)J.first[J.n], 128, 0, s>>>(J);
     MOPA_LAUNCHED();
+    J.n = 0;
     return 0;
 }
 
@@ -481,21 +513,35 @@ __global__ void k_rule_offsets(const int32_t *__restrict__ rank, const int32_t *
 }
 
 // ------------------------------------------------------------------------------------------------ Metadata ops
-int ensure_subm(mopa_scn_metadata *m, int level, cudaStream_t s) {
+int ensure_subm_many(mopa_scn_metadata *m, const int *levels, int n, cudaStream_t s) {
     MOPA_TRY(finish_levels(m, s));
-    Level &L = m->levels[level];
-    if (L.nbr) return 0;
-    L.nbr_ld = round_up(L.V > 0 ? L.V : 1, 32);
-    MOPA_TRY(meta_alloc(m, (void **)&L.nbr, (size_t)27 * L.nbr_ld * 4, s));
-    MOPA_CHECK(L.V < ((int64_t)1 << kTileRowShift), "more than 2^25 active sites at one level: tile rulebook entries overflow");
-    const int64_t tiles = ceil_div(L.V > 0 ? L.V : 1, kTileRows);
-    MOPA_TRY(meta_alloc(m, (void **)&L.tl_subm, (size_t)tiles * 27 * kTileRows * 4, s));
-    MOPA_TRY(meta_alloc(m, (void **)&L.tm_subm, (size_t)tiles * 27 * sizeof(uint4), s));
-    k_subm_tiles<<<dim3((unsigned)tiles, 27), 128, 0, s>>>(L.keys, L.V, (int)L.spatial, L.tab_keys, L.tab_vals, L.cap - 1, L.nbr,
-                                                          L.nbr_ld, L.tl_subm, L.tm_subm);
-    MOPA_LAUNCHED();
+    GeoJobs J{};
+    for (int i = 0; i < n; ++i) {
+        Level &L = m->levels[levels[i]];
+        if (L.nbr) continue;
+        if (J.n == kGeoMaxJobs) {
+            k_subm_tiles_batch<<<(unsigned)J.first[J.n], 128, 0, s>>>(J);
+            MOPA_LAUNCHED();
+            J = GeoJobs{};
+        }
+        L.nbr_ld = round_up(L.V > 0 ? L.V : 1, 32);
+        MOPA_TRY(meta_alloc(m, (void **)&L.nbr, (size_t)27 * L.nbr_ld * 4, s));
+        MOPA_CHECK(L.V < ((int64_t)1 << kTileRowShift), "more than 2^25 active sites at one level: tile rulebook entries overflow");
+        const int64_t tiles = ceil_div(L.V > 0 ? L.V : 1, kTileRows);
+        MOPA_TRY(meta_alloc(m, (void **)&L.tl_subm, (size_t)tiles * 27 * kTileRows * 4, s));
+        MOPA_TRY(meta_alloc(m, (void **)&L.tm_subm, (size_t)tiles * 27 * sizeof(uint4), s));
+        const int j = J.n++;
+        J.keys[j] = L.keys; J.V[j] = L.V; J.spatial[j] = (int)L.spatial; J.tab_keys[j] = L.tab_keys; J.tab_vals[j] = L.tab_vals;
+        J.mask[j] = (uint32_t)(L.cap - 1); J.nbr[j] = L.nbr; J.ld[j] = L.nbr_ld; J.out[j] = L.tl_subm; J.tm[j] = L.tm_subm;
+        J.first[j + 1] = J.first[j] + (int)(tiles * 27);
+    }
+    if (J.n) {
+        k_subm_tiles_batch<<<(unsigned)J.first[J.n], 128, 0, s>>>(J);
+        MOPA_LAUNCHED();
+    }
     return 0;
 }
+int ensure_subm(mopa_scn_metadata *m, int level, cudaStream_t s) { return ensure_subm_many(m, &level, 1, s); }
 
 static int read_back(mopa_scn_metadata *m, const int32_t *dev, int n_ints, cudaStream_t s) {
     MOPA_CUDA(cudaMemcpyAsync(m->pinned, dev, (size_t)n_ints * 4, cudaMemcpyDeviceToHost, s));
@@ -552,20 +598,40 @@ int finish_levels(mopa_scn_metadata *m, cudaStream_t s) {
     for (int l = first; l < n_lv; ++l)
         if (m->levels[l].V < 0) m->levels[l].V = m->pinned[l];
     MOPA_CHECK(m->pinned[31] == 0, "InputLayer: coordinates outside [0, spatial_size) or batch index outside [0, 65535)");
+    // every link's child table in one block (one fill, one scatter launch), then every strided tile rulebook in one launch
+    std::vector<int> todo;
+    size_t child_ints = 0;
     for (int l = (first > 0 ? first - 1 : 0); l + 1 < n_lv; ++l) {
         Level &L = m->levels[l];
-        Level &N = m->levels[l + 1];
         if (!L.has_down || L.child) continue;
-        const int64_t Vf = L.V;
-        L.child_ld = round_up(N.V > 0 ? N.V : 1, 32);
-        MOPA_TRY(meta_alloc(m, (void **)&L.child, (size_t)8 * L.child_ld * 4, s));
-        MOPA_CUDA(cudaMemsetAsync(L.child, 0xFF, (size_t)8 * L.child_ld * 4, s));
-        if (Vf > 0) {
-            k_child_scatter<<<(unsigned)ceil_div(Vf, 256), 256, 0, s>>>(L.parent, L.kidx, Vf, L.child, L.child_ld);
+        L.child_ld = round_up(m->levels[l + 1].V > 0 ? m->levels[l + 1].V : 1, 32);
+        child_ints += (size_t)8 * L.child_ld;
+        todo.push_back(l);
+    }
+    if (todo.empty()) return 0;
+    int32_t *block = nullptr;
+    MOPA_TRY(meta_alloc(m, (void **)&block, child_ints * 4, s));
+    MOPA_CUDA(cudaMemsetAsync(block, 0xFF, child_ints * 4, s));
+    for (size_t b = 0; b < todo.size(); b += kGeoMaxJobs / 2) {  // two tile rulebooks per link
+        GeoJobs S{}, T{};
+        for (size_t i = b; i < todo.size() && i < b + kGeoMaxJobs / 2; ++i) {
+            Level &L = m->levels[todo[i]];
+            Level &N = m->levels[todo[i] + 1];
+            L.child = block;
+            block += (size_t)8 * L.child_ld;
+            if (L.V > 0) {
+                const int j = S.n++;
+                S.parent[j] = L.parent; S.kidx[j] = L.kidx; S.V[j] = L.V; S.out[j] = L.child; S.ld[j] = L.child_ld;
+                S.first[j + 1] = S.first[j] + (int)ceil_div(L.V, 256);
+            }
+            MOPA_TRY(add_tile_job(m, T, L.child, L.child_ld, nullptr, nullptr, N.V, L.V, 8, &L.tl_child, &L.tm_child, s));
+            MOPA_TRY(add_tile_job(m, T, nullptr, 0, L.parent, L.kidx, L.V, N.V, 8, &L.tl_sel, &L.tm_sel, s));
+        }
+        if (S.n) {
+            k_child_scatter_batch<<<(unsigned)S.first[S.n], 256, 0, s>>>(S);
             MOPA_LAUNCHED();
         }
-        MOPA_TRY(build_tile_lists(m, L.child, L.child_ld, nullptr, nullptr, N.V, Vf, 8, &L.tl_child, &L.tm_child, s));
-        MOPA_TRY(build_tile_lists(m, nullptr, 0, L.parent, L.kidx, Vf, N.V, 8, &L.tl_sel, &L.tm_sel, s));
+        MOPA_TRY(flush_tile_jobs(T, s));
     }
     return 0;
 }

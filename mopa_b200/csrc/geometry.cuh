@@ -78,12 +78,20 @@ struct Gather {
     int op = 0;         // 1 submanifold, 2 convolution, 3 deconvolution (profiling tag only)
 };
 
+// d_input pass whose output is the gradient of a BatchNormReLU's output: what the conv epilogue needs to reduce the two
+// per-column sums of that BatchNorm's backward pass (x = the BatchNorm's INPUT; planes = the conv's output channels)
+struct TcBnBwd {
+    const float *x;
+    int64_t ld_x;
+    const float *mean, *invstd, *weight, *bias;
+    float leak;
+};
 int meta_alloc(mopa_scn_metadata *m, void **p, size_t bytes, cudaStream_t s);
 int set_locations(mopa_scn_metadata *m, int64_t spatial_size, const int64_t *coords, int64_t n, int ncols,
                   int coords_on_device, cudaStream_t s, bool defer_sync = false);
 int conv_apply(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *weight,
                const float *packed, int n_in0, int n_out0, int transpose, int flip, int precision, cudaStream_t s,
-               double *stats = nullptr, bool *stats_done = nullptr);
+               double *stats = nullptr, bool *stats_done = nullptr, const TcBnBwd *bn = nullptr);
 int conv_dweight(const Gather &gt, const float *in, int64_t ld_in, const float *dout, int64_t ld_dout, float *dw,
                  int n_in, int n_out, int precision, void *workspace, size_t workspace_bytes, cudaStream_t s);
 size_t dw_workspace_bytes(int volume, int n_in, int n_out, int64_t n_rows);
@@ -110,7 +118,7 @@ struct TcPackJobs {
 int pack_weights_tc_batch(TcPackJobs &jobs, int n_jobs, cudaStream_t s);
 bool conv_packs_tc(int c_in, int c_out, int precision);  // this shape's weights go through pack_weights_tc
 int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, int64_t ld_out, const float *packed,
-                  int c_in, int c_out, double *stats, cudaStream_t s);
+                  int c_in, int c_out, double *stats, cudaStream_t s, const TcBnBwd *bn = nullptr);
 // tcgen05 d_weight (conv_dw_tc.cu): TF32 mode, channel counts that are multiples of 16
 bool dw_tc_enabled();
 bool dw_tc_supported(int n_in, int n_out);
@@ -128,9 +136,10 @@ constexpr int kStatsLd = 256;  // per-buffer statistics block: [sum x | sum x^2]
 int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, const float *d_out, int64_t ld_dout,
                 const float *save_mean, const float *save_invstd, const float *weight, const float *bias, float *d_weight,
                 float *d_bias, float leakiness, int train, int64_t n_active, int planes, void *workspace, int accumulate,
-                cudaStream_t s);
+                cudaStream_t s, const double *sums = nullptr);
 size_t bn_workspace_bytes(int planes);
 int ensure_subm(mopa_scn_metadata *m, int level, cudaStream_t s);
+int ensure_subm_many(mopa_scn_metadata *m, const int *levels, int n, cudaStream_t s);  // one launch for all of them
 int ensure_down(mopa_scn_metadata *m, int level, cudaStream_t s);
 int ensure_down_async(mopa_scn_metadata *m, int level, cudaStream_t s);  // hashes level + 1 without a host round trip
 int finish_levels(mopa_scn_metadata *m, cudaStream_t s);                  // ONE synchronisation: all pending counts

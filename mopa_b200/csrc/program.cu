@@ -34,7 +34,7 @@ struct Layout {  // resolved per forward from the level sizes
     std::vector<int64_t> buf_ld;   // row stride (floats) of every buffer
     std::vector<size_t> bn_off;    // per op: byte offset of (save_mean, save_invstd) in the activation arena
     std::vector<size_t> pk_off;    // per conv op: byte offset of its packed weights in the scratch block
-    size_t act_bytes = 0, grad_bytes = 0, packed_bytes = 0, dw_bytes = 0;
+    size_t act_bytes = 0, grad_bytes = 0, packed_bytes = 0, dw_bytes = 0, stats_bytes = 0;
 };
 
 static std::mutex g_stream_mu;
@@ -136,6 +136,7 @@ static int make_layout(const mopa_scn_program *p, const mopa_scn_metadata *m, in
     // forward reuses the d_weight workspace for the BatchNorm statistics blocks (one per buffer, conv epilogue -> BN)
     const size_t stats_bytes = align256(nb * (size_t)2 * kStatsLd * sizeof(double));
     if (stats_bytes > L.dw_bytes) L.dw_bytes = stats_bytes;
+    L.stats_bytes = stats_bytes;  // backward: its own block behind the d_weight workspace (which is busy on the side stream)
     L.act_bytes = off + 256;
     return 0;
 }
@@ -252,8 +253,10 @@ int mopa_scn_Program_prepare(mopa_scn_program *p, mopa_scn_metadata *m, const in
     bool need_subm[32] = {false};
     for (const POp &o : p->ops)
         if (o.type == OP_SUBM) need_subm[o.level_in] = true;
+    int subm_levels[32], n_subm = 0;
     for (int l = 0; l < p->n_levels; ++l)
-        if (need_subm[l]) MOPA_TRY(ensure_subm(m, l, gs));
+        if (need_subm[l]) subm_levels[n_subm++] = l;
+    MOPA_TRY(ensure_subm_many(m, subm_levels, n_subm, gs));
     if (!m->geom_done) MOPA_CUDA(cudaEventCreateWithFlags(&m->geom_done, cudaEventDisableTiming));
     MOPA_CUDA(cudaEventRecord(m->geom_done, gs));
     MOPA_CUDA(cudaStreamWaitEvent(main, m->geom_done, 0));
@@ -262,7 +265,7 @@ int mopa_scn_Program_prepare(mopa_scn_program *p, mopa_scn_metadata *m, const in
     for (int l = 0; l < p->n_levels; ++l) n_active_out[l] = m->levels[l].V;
     sizes_out[0] = L.act_bytes;
     sizes_out[1] = L.grad_bytes;
-    sizes_out[2] = L.packed_bytes + L.dw_bytes;
+    sizes_out[2] = L.packed_bytes + L.dw_bytes + L.stats_bytes;
     return 0;
 }
 
@@ -360,6 +363,30 @@ int mopa_scn_Program_backward(mopa_scn_program *p, mopa_scn_metadata *m, const v
         if (p->fork_events.size() != p->ops.size()) p->fork_events.assign(p->ops.size(), nullptr);
         if (!p->join_event) MOPA_CUDA(cudaEventCreateWithFlags(&p->join_event, cudaEventDisableTiming));
     }
+    // BatchNorm backward sums ride on the epilogue of the d_input convolution that produces the BatchNorm's output
+    // gradient (tcgen05 kernel): one [S1 | S2] block per buffer; the BatchNorm backward is then a single streaming kernel
+    const char *nofuse = getenv("MOPA_SCN_NO_BNSTATS_FUSION");  // read per call, as in the forward pass
+    // Off by default: measured (profiles/r02_bn_bwd_fusion.txt) the epilogue work costs the d_input kernels what the
+    // BatchNorm statistics kernels save, and d_input time is harder to overlap with the d_weight stream than BatchNorm time.
+    // MOPA_SCN_BNBWD_FUSION=1 turns it on.
+    const char *fuse_b = getenv("MOPA_SCN_BNBWD_FUSION");
+    const bool fuse_stats = !(nofuse && nofuse[0] == '1') && (fuse_b && fuse_b[0] == '1');
+    double *bwd_stats = reinterpret_cast<double *>(reinterpret_cast<char *>(scratch) + L.packed_bytes + L.dw_bytes);
+    std::vector<char> sums_ok(nb, 0);
+    std::vector<int> bn_of(nb, -1);  // buffer -> the BatchNorm op that wrote it in the forward pass
+    if (fuse_stats) {
+        MOPA_CUDA(cudaMemsetAsync(bwd_stats, 0, nb * (size_t)2 * kStatsLd * sizeof(double), s));
+        for (size_t i = 0; i < p->ops.size(); ++i)
+            if (p->ops[i].type == OP_BN && p->bufs[p->ops[i].out].parent < 0) bn_of[p->ops[i].out] = (int)i;
+        // only where ONE op reads the BatchNorm's output (a second reader would add to the gradient after the sums)
+        std::vector<int> readers(nb, 0);
+        for (const POp &o : p->ops) {
+            ++readers[o.in];
+            if (p->bufs[o.in].parent >= 0) ++readers[p->bufs[o.in].parent];
+        }
+        for (size_t b = 0; b < nb; ++b)
+            if (readers[b] != 1 || (int)b == p->out_buf) bn_of[b] = -1;
+    }
     BufView g_last = view(L, grad_arena, p->out_buf);
     MOPA_TRY(mopa_scn_OutputLayer_updateGradInput(m, g_last.ptr, g_last.ld, d_out, ld_dout, p->bufs[p->out_buf].channels, s));
     mark(p->out_buf);
@@ -385,7 +412,8 @@ int mopa_scn_Program_backward(mopa_scn_program *p, mopa_scn_metadata *m, const v
             MOPA_TRY(bn_backward(x.ptr, x.ld, need_din ? dx.ptr : nullptr, dx.ld, dy.ptr, dy.ld, save, save + o.n_in,
                                  (const float *)params[o.param], (const float *)params[o.param + 1],
                                  (float *)param_grads[o.param], (float *)param_grads[o.param + 1], o.leak, train,
-                                 m->levels[o.level_in].V, o.n_in, p->bn_ws, accumulate, s));
+                                 m->levels[o.level_in].V, o.n_in, p->bn_ws, accumulate, s,
+                                 sums_ok[o.out] ? bwd_stats + (size_t)o.out * 2 * kStatsLd : nullptr));
         } else {
             const float *w = (const float *)params[o.param];
             // d_weight first: it is forked to its own stream and overlaps the d_input kernel of the same op
@@ -405,8 +433,23 @@ int mopa_scn_Program_backward(mopa_scn_program *p, mopa_scn_metadata *m, const v
                                       : nullptr;
                 Gather g = op_gather(o, m, true);
                 g.accumulate = accumulate;
+                // this op is the only producer of d(o.in), and o.in is the output of a BatchNormReLU: reduce that
+                // BatchNorm's backward sums while the gradient rows are still in registers
+                const int bi = accumulate ? -1 : bn_of[o.in];
+                TcBnBwd bn{};
+                double *sums = nullptr;
+                bool done = false;
+                if (bi >= 0 && p->ops[bi].n_in == o.n_in && o.n_in <= kStatsLd) {
+                    const POp &b = p->ops[bi];
+                    const float *save = reinterpret_cast<const float *>(reinterpret_cast<const char *>(act) + L.bn_off[bi]);
+                    BufView bx = view(L, act, b.in);
+                    bn = TcBnBwd{bx.ptr, bx.ld, save, save + b.n_in, (const float *)params[b.param],
+                                 (const float *)params[b.param + 1], b.leak};
+                    sums = bwd_stats + (size_t)o.in * 2 * kStatsLd;
+                }
                 MOPA_TRY(conv_apply(g, dy.ptr, dy.ld, dx.ptr, dx.ld, w, pk, o.n_in, o.n_out, 1, o.type == OP_SUBM ? 1 : 0,
-                                    precision, s));
+                                    precision, s, sums, &done, sums ? &bn : nullptr));
+                if (sums && done) sums_ok[o.in] = 1;
             }
         }
         if (need_din) mark(o.in);

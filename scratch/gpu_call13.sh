@@ -1,4 +1,14 @@
 #!/bin/bash
 O=gpurun_out; mkdir -p $O
 T="timeout -k 5"
-$T 900 python -m pytest tests -m gpu -q 2>&1 | tail -40 > $O/c13_tests.log; grep -E "passed|failed|FAILED|assert|Error" $O/c13_tests.log | head -40
+$T 180 python -c "import __graft_entry__ as g; g.smoke()" > $O/c25_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/c25_smoke.log
+for cfg in "X=0" "MOPA_TC_BN_RING=0" "MOPA_TC_BN_RING=-1"; do
+  tag="${cfg// /_}"
+  env $cfg $T 200 python tools/layer_table.py --out "$O/c25_layers_$tag.json" > "$O/c25_layers_$tag.log" 2>&1; echo "== $cfg"; tail -6 "$O/c25_layers_$tag.log" | grep -E "dinput|bn_bwd|conv_fwd"
+  f="$O/c25_bench_$tag.json"
+  env $cfg $T 150 python bench.py --no-cpu-baseline --no-roofline --no-fp32 --steps 50 > "$f" 2>$O/c25_err.txt; echo "$cfg: $(python -c "import json,sys; d=json.load(open('$f')); print('%.3f ms/step  e2e %.3f' % (d['ms_per_step'], d['e2e']['ms_per_step']))" 2>&1 | tail -1)"
+done
+export MOPA_SCN_LIB=$PWD/scratch/bin/libmopa_scn_trace.so
+for cfg in "X=0" "MOPA_TC_BN_RING=0"; do
+  echo "== trace $cfg"; env $cfg $T 120 python scratch/tc_trace3.py 2>&1 | tail -1
+done

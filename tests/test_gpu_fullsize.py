@@ -99,7 +99,7 @@ def test_every_rulebook_of_a_full_batch_is_bit_exact(scn, sensor, batch):
 
 
 def test_tile_rulebooks_agree_with_the_dense_tables(scn):
-    """The per-(128-row tile, offset) compact lists + row masks the tcgen05 conv kernel consumes (geometry.cu::k_tile_lists)
+    """The per-(128-row tile, offset) compact lists + row masks the tcgen05 conv kernel consumes (geometry.cu::k_tile_lists_batch)
     against the dense neighbour / child / parent tables they are built from, through the inspection entry point."""
     coords, feats = synth.make_batch(2, "nuscenes", 5, n_azimuth=400)
     x = scn.InputLayer(3, 4096, mode=4)([torch.from_numpy(coords), torch.from_numpy(feats).cuda()])
