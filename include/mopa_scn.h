@@ -181,7 +181,10 @@ mopa_scn_program *mopa_scn_Program_new(const int32_t *ops, int n_ops, const int3
 void mopa_scn_Program_delete(mopa_scn_program *p);
 /* voxelise `coords` (as InputLayer_setLocations) and build every grid / table the program needs on a dedicated
  * high-priority stream; `stream` is made to wait for it. n_active_out[n_levels]; sizes_out = {activation arena bytes,
- * gradient arena bytes, scratch bytes}. */
+ * gradient arena bytes, scratch bytes}. coords_on_device: 0 host pointer; 1 device pointer whose contents may still be
+ * in flight on `stream` (the geometry stream waits for everything queued there); 2 device pointer whose contents are
+ * complete (no wait: the geometry of this forward overlaps whatever `stream` is still running, e.g. the previous
+ * step's backward pass). */
 int mopa_scn_Program_prepare(mopa_scn_program *p, mopa_scn_metadata *m, const int64_t *coords, int64_t n, int ncols,
                              int coords_on_device, int precision, void *stream, int64_t *n_active_out,
                              uint64_t *sizes_out);

@@ -247,6 +247,9 @@ __global__ void __launch_bounds__(1024) k_unique_scan(const int32_t *__restrict_
     __syncthreads();
     const int bid = s_bid;
     const int64_t n_eff = n_dev ? min(n, (int64_t)*n_dev) : n;
+    // launches are sized by an upper bound of n: blocks past the true count leave at once (nobody waits for them: a block
+    // only looks back at lower indices, and every block below a working block is a working block)
+    if (bid > 0 && (int64_t)bid * 1024 >= n_eff) return;
     const int64_t i = (int64_t)bid * 1024 + threadIdx.x;
     int slot = -1, flag = 0;
     if (i < n_eff) {
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(1024) k_unique_scan(const int32_t *__restrict_
             atomicExch(status + bid, (2ull << 62) | (prefix + total));
         }
         s_prefix = (int)prefix;
-        if ((int64_t)(bid + 1) * 1024 >= n) *count_out = (int)(prefix + total);  // the last block of the launch
+        if ((int64_t)(bid + 1) * 1024 >= n_eff) *count_out = (int)(prefix + total);  // the block that holds the last element
     }
     __syncthreads();
     if (flag) {

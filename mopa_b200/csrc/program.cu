@@ -240,14 +240,14 @@ int mopa_scn_Program_prepare(mopa_scn_program *p, mopa_scn_metadata *m, const in
     MOPA_CUDA(cudaSetDevice(m->device));
     MOPA_TRY(geom_stream(m->device, &gs));
     m->last_stream = main;
-    if (coords_on_device) {  // the coordinates may have been produced on the caller's stream
+    if (coords_on_device == 1) {  // the coordinates may have been produced on the caller's stream (2: known complete)
         if (!m->geom_done) MOPA_CUDA(cudaEventCreateWithFlags(&m->geom_done, cudaEventDisableTiming));
         MOPA_CUDA(cudaEventRecord(m->geom_done, main));
         MOPA_CUDA(cudaStreamWaitEvent(gs, m->geom_done, 0));
     }
     // the whole pyramid is hashed back to back; ONE host round trip brings every level's site count (and the coordinate
     // error flag) back, instead of one per level
-    MOPA_TRY(set_locations(m, p->spatial, coords, n, ncols, coords_on_device, gs, /*defer_sync=*/true));
+    MOPA_TRY(set_locations(m, p->spatial, coords, n, ncols, coords_on_device != 0, gs, /*defer_sync=*/true));
     for (int l = 0; l + 1 < p->n_levels; ++l) MOPA_TRY(ensure_down_async(m, l, gs));
     MOPA_TRY(finish_levels(m, gs));
     bool need_subm[32] = {false};

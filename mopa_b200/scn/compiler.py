@@ -209,6 +209,7 @@ class _ProgramFunction(Function):
         dev = feats.device
         handle = prog.ensure_handle(dev.index if dev.index is not None else torch.cuda.current_device())
         meta = F.Metadata(3, dev)
+        where = F._coords_where(coords)
         if coords.dtype != torch.int64:
             coords = coords.long()
         coords = coords.contiguous()
@@ -223,8 +224,8 @@ class _ProgramFunction(Function):
         n_active = (ctypes.c_int64 * prog.n_levels)()
         sizes = (ctypes.c_uint64 * 3)()
         with torch.cuda.device(dev):
-            _lib.check(L.mopa_scn_Program_prepare(handle, meta._h, coords.data_ptr(), n, ncols, 1 if coords.is_cuda else 0,
-                                                  prec, stream, n_active, sizes))
+            _lib.check(L.mopa_scn_Program_prepare(handle, meta._h, coords.data_ptr(), n, ncols, where, prec, stream, n_active,
+                                                  sizes))
             meta.n_points = n
             act = torch.empty(sizes[0], dtype=torch.uint8, device=dev)
             scratch = torch.empty(sizes[2], dtype=torch.uint8, device=dev)

@@ -43,6 +43,20 @@ def _stream(device=None):
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def _coords_where(coords):
+    """coords_on_device argument of the C ABI: 0 host tensor, 1 device tensor (the geometry stream waits for the caller's
+    stream), 2 device tensor known to be complete: it carries the event of the copy that produced it
+    (mopa_b200.data.DevicePrefetcher / mark_ready) and is passed on as it is, so the geometry of this forward may overlap
+    whatever the caller's stream is still running."""
+    if not coords.is_cuda:
+        return 0
+    ready = getattr(coords, "_mopa_ready", None)
+    if ready is None or coords.dtype != torch.int64 or not coords.is_contiguous():
+        return 1
+    ready.synchronize()  # recorded a step ago: returns at once
+    return 2
+
+
 def _on_device(fn):
     """Runs an autograd Function's forward / backward with the device of its first CUDA tensor argument current, so
     that allocations, the stream handle (_stream()) and the library's cudaSetDevice all agree, and the caller's current

@@ -1,10 +1,11 @@
 #!/bin/bash
 O=gpurun_out; mkdir -p $O
 T="timeout -k 5"
-$T 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/c17_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/c17_smoke.log
-if ! grep -q "xm operators ok" $O/c17_smoke.log; then echo "SMOKE FAILED - stopping"; cat $O/c17_smoke.log | tail -20; exit 1; fi
-$T 900 python -m pytest tests -m gpu -q 2>&1 | tail -8 > $O/c17_tests.log; grep -E "passed|failed|FAILED" $O/c17_tests.log
-for sensor in nuscenes kitti; do
-  f="$O/c17_bench_${sensor}.json"
-  $T 200 python bench.py --sensor $sensor --no-cpu-baseline --no-fp32 --steps 50 --warmup 10 > "$f" 2>$O/c17_err.txt; echo "$sensor: $(python -c "import json,sys; d=json.load(open('$f')); print('%.3f ms/step (median %.3f) e2e %.3f (median %.3f) geometry %.3f ms launches/step %.0f' % (d['ms_per_step'], d['step_ms']['median'], d['e2e']['ms_per_step'], d['e2e']['median_ms'], d['geometry']['ms_per_forward'], d['gpu_launches']/d['steps']))" 2>&1 | tail -1)"
+$T 180 python -c "import __graft_entry__ as g; g.smoke()" > $O/c28_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/c28_smoke.log
+if ! grep -q "^smoke:" $O/c28_smoke.log; then echo "SMOKE FAILED - stopping"; tail -30 $O/c28_smoke.log; exit 1; fi
+for rep in 1 2; do
+  f="$O/c28_bench_$rep.json"
+  $T 200 python bench.py --no-cpu-baseline --no-roofline --no-fp32 --steps 60 > "$f" 2>$O/c28_err.txt; echo "default: $(python -c "import json,sys; d=json.load(open('$f')); print('%.3f ms/step median %.3f | e2e %.3f median %.3f | sync loop %.3f' % (d['ms_per_step'], d['step_ms']['median'], d['e2e']['ms_per_step'], d['e2e']['median_ms'], d['e2e']['sync_loop']['ms_per_step']))" 2>&1 | tail -1)"
 done
+tail -3 $O/c28_err.txt
+$T 900 python -m pytest tests -x -q -m gpu > $O/c28_tests.log 2>&1; echo "tests rc=$?"; tail -5 $O/c28_tests.log
