@@ -397,6 +397,7 @@ def run_ours(a):
         return {"sec": max(r[0] for r in rows) * 1e-3, "pts": sum(r[4] for r in rows), "launches": _lib.kernel_launches() - l0,
                 "window": (t0, t1), "median_ms": max(r[1] for r in rows), "p10_ms": max(r[2] for r in rows),
                 "p90_ms": max(r[3] for r in rows), "max_ms": max(r[5] for r in rows),
+                "slow_steps": [(int(i), round(float(per[i]), 3)) for i in np.argsort(per)[::-1][:4] if per[i] > 1.25 * np.median(per)],
                 "per_rank": [{"ms_per_step": r[0] / steps, "median_ms": r[1], "points_per_step": r[4] / steps} for r in rows]}
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -442,6 +443,7 @@ def run_ours(a):
                        "storage": "fp32 features/grads, tf32 tensor-core products, fp32 accumulate" if a.precision == "tf32"
                                   else "fp32 storage, 3xTF32 split products (fp32-equivalent)"},
             "step_ms": {"median": res["median_ms"], "p10": res["p10_ms"], "p90": res["p90_ms"], "max": res["max_ms"],
+                        "slow_steps_rank0": res["slow_steps"],
                         "note": "per-step CUDA-event times inside the same timed region; max over ranks"},
             "e2e": {"value": e2e["pts"] / e2e["sec"], "unit": UNIT, "ms_per_step": 1e3 * e2e["sec"] / a.steps,
                     "median_ms": e2e["median_ms"], "p90_ms": e2e["p90_ms"], "max_ms": e2e["max_ms"],

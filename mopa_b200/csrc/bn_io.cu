@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(256) k_bn_stats(const float *__restrict__ x, i
                                                   float *__restrict__ running_mean, float *__restrict__ running_var,
                                                   float *__restrict__ d_weight, float *__restrict__ d_bias) {
     extern __shared__ float sred[];  // [blockDim.y][2 * planes]
+    pdl_wait();  // (launched through launch_pdl: x / dout come from the previous kernel in the stream)
+    pdl_trigger();
     const int c0 = threadIdx.x * VEC;
     float s1[VEC], s2[VEC], ref[VEC], sc[VEC], sh[VEC];
 #pragma unroll
@@ -195,6 +197,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float *__restrict__ 
                                                       const float *__restrict__ ws, float leakiness, int accumulate,
                                                       const double *__restrict__ sums, int train,
                                                       float *__restrict__ d_weight, float *__restrict__ d_bias, float inv_n) {
+    pdl_wait();
+    pdl_trigger();
     const int c0 = threadIdx.x * VEC;
     float sc[VEC], sh[VEC], mu[VEC], gm[VEC], kk[VEC];
 #pragma unroll
@@ -441,6 +445,8 @@ __global__ void __launch_bounds__(256) k_bn_apply_sums(const float *__restrict__
                                                        float momentum, float *__restrict__ save_mean,
                                                        float *__restrict__ save_invstd, float *__restrict__ running_mean,
                                                        float *__restrict__ running_var, double inv_n) {
+    pdl_wait();
+    pdl_trigger();
     const int c0 = threadIdx.x * VEC;
     const double dn = (double)n;
     float sc[VEC], sh[VEC];
@@ -640,9 +646,9 @@ int bn_forward(const float *in, int64_t ld_in, float *out, int64_t ld_out, float
     float *ws = reinterpret_cast<float *>(workspace);
     const int prof = prof_begin(40, nullptr, planes, planes, n_active, s);
     if (train && stats && sh.vec == 4) {  // the producing convolution accumulated the column sums in its epilogue
-        k_bn_apply_sums<4><<<sh.grid, sh.block, 0, s>>>(in, ld_in, out, ld_out, n_active, planes, stats, weight, bias, leakiness,
-                                                        eps, momentum, save_mean, save_invstd, running_mean, running_var,
-                                                        1.0 / (double)n_active);
+        MOPA_CUDA(launch_pdl(k_bn_apply_sums<4>, dim3(sh.grid), sh.block, 0, s, in, ld_in, out, ld_out, n_active, planes, stats,
+                             weight, bias, leakiness, eps, momentum, save_mean, save_invstd, running_mean, running_var,
+                             1.0 / (double)n_active));
         MOPA_LAUNCHED();
         prof_end(prof, s);
         return 0;
@@ -697,9 +703,9 @@ int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, con
     float *ws = reinterpret_cast<float *>(workspace);
     const int prof = prof_begin(50, nullptr, planes, planes, n_active, s);
     if (sums && d_in && sh.vec == 4) {  // the producing d_input convolution reduced the column sums in its epilogue
-        k_bn_bwd_apply<4><<<sh.grid, sh.block, 0, s>>>(in, ld_in, d_out, ld_dout, d_in, ld_din, n_active, planes, save_mean,
-                                                       save_invstd, weight, bias, ws, leakiness, accumulate, sums, train,
-                                                       d_weight, d_bias, (float)(1.0 / (double)n_active));
+        MOPA_CUDA(launch_pdl(k_bn_bwd_apply<4>, dim3(sh.grid), sh.block, 0, s, in, ld_in, d_out, ld_dout, d_in, ld_din, n_active,
+                             planes, save_mean, save_invstd, weight, bias, (const float *)ws, leakiness, accumulate, sums, train,
+                             d_weight, d_bias, (float)(1.0 / (double)n_active)));
         MOPA_LAUNCHED();
         prof_end(prof, s);
         return 0;
@@ -712,9 +718,9 @@ int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, con
         return rc;
     }
     if (sh.vec == 4)
-        k_bn_stats<4, true><<<sh.grid, sh.block, sh.smem, s>>>(in, ld_in, d_out, ld_dout, n_active, planes, ws, save_mean,
-                                                               save_invstd, weight, bias, leakiness, train, 0.f, 0.f,
-                                                               nullptr, nullptr, nullptr, nullptr, d_weight, d_bias);
+        MOPA_CUDA(launch_pdl(k_bn_stats<4, true>, dim3(sh.grid), sh.block, sh.smem, s, in, ld_in, d_out, ld_dout, n_active, planes,
+                             ws, save_mean, save_invstd, weight, bias, leakiness, train, 0.f, 0.f, (float *)nullptr,
+                             (float *)nullptr, (float *)nullptr, (float *)nullptr, d_weight, d_bias));
     else
         k_bn_stats<1, true><<<sh.grid, sh.block, sh.smem, s>>>(in, ld_in, d_out, ld_dout, n_active, planes, ws, save_mean,
                                                                save_invstd, weight, bias, leakiness, train, 0.f, 0.f,
@@ -722,9 +728,9 @@ int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, con
     MOPA_LAUNCHED();
     if (d_in) {
         if (sh.vec == 4)
-            k_bn_bwd_apply<4><<<sh.grid, sh.block, 0, s>>>(in, ld_in, d_out, ld_dout, d_in, ld_din, n_active, planes,
-                                                           save_mean, save_invstd, weight, bias, ws, leakiness, accumulate,
-                                                           nullptr, train, nullptr, nullptr, 0.f);
+            MOPA_CUDA(launch_pdl(k_bn_bwd_apply<4>, dim3(sh.grid), sh.block, 0, s, in, ld_in, d_out, ld_dout, d_in, ld_din,
+                                 n_active, planes, save_mean, save_invstd, weight, bias, (const float *)ws, leakiness, accumulate,
+                                 (const double *)nullptr, train, (float *)nullptr, (float *)nullptr, 0.f));
         else
             k_bn_bwd_apply<1><<<sh.grid, sh.block, 0, s>>>(in, ld_in, d_out, ld_dout, d_in, ld_din, n_active, planes,
                                                            save_mean, save_invstd, weight, bias, ws, leakiness, accumulate,

@@ -3,10 +3,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <utility>
 
 namespace mopa {
 
@@ -42,6 +44,34 @@ inline int fail(const char *file, int line, const std::string &msg) {
         if (e__ != cudaSuccess)                                                           \
             return ::mopa::fail(__FILE__, __LINE__, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
     } while (0)
+
+// ---- programmatic dependent launch. The network is a chain of ~180 dependent kernels per step on one stream; between two
+// plain launches the GPU drains, then starts the next grid (a few microseconds each). A kernel launched through
+// launch_pdl may begin while its predecessor in the stream is still running: its blocks run their prologue (barrier
+// initialisation, TMEM allocation, loads of data that is older than the predecessor), then pdl_wait() blocks until the
+// predecessor grid has completed and its writes are visible. pdl_trigger() lets the NEXT kernel in the stream start
+// launching. Rules kept by every kernel that uses them: pdl_wait() before the first access to anything the predecessor
+// may write, pdl_trigger() after it (so at most one dependent grid is ever waiting), both executed by all threads.
+// Launched without the attribute (the default; MOPA_SCN_PDL=1 sets it) both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("MOPA_SCN_PDL");  // off by default: measured no gain (profiles/r02_overlap.txt): the gaps of the
+        return e && e[0] == '1';                  // main stream are already filled by the d_weight and geometry streams
+    }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 constexpr int kNumSMs = 148;  // B200; used where a work plan must be reproducible without a device (d_weight items)
 

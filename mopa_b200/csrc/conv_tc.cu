@@ -208,6 +208,10 @@ __global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    // everything above read only the tile rulebook and per-channel constants (older than the previous kernel in the stream);
+    // from here on the activations / gradients it wrote are read
+    pdl_wait();
+    pdl_trigger();
     TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2, 7, 1);
 
     if (warp < 8) {
@@ -734,11 +738,11 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
 #define MOPA_TC_GO(NA_, LPR_, W_)                                                                                              \
     do {                                                                                                                       \
         if (bnk)                                                                                                               \
-            k_conv_tc<NA_, LPR_, W_, true><<<grid, threads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb,   \
-                                                                       tpc, gw, acc, stats, X);                                \
+            MOPA_CUDA(launch_pdl(k_conv_tc<NA_, LPR_, W_, true>, grid, dim3(threads), smem, s, gt, in, ld_in, out, ld_out,    \
+                                 packed, c_in, nt, sa, sb, tpc, gw, acc, stats, X));                                           \
         else                                                                                                                   \
-            k_conv_tc<NA_, LPR_, W_, false><<<grid, threads, smem, s>>>(gt, in, ld_in, out, ld_out, packed, c_in, nt, sa, sb,  \
-                                                                        tpc, gw, acc, stats, X);                               \
+            MOPA_CUDA(launch_pdl(k_conv_tc<NA_, LPR_, W_, false>, grid, dim3(threads), smem, s, gt, in, ld_in, out, ld_out,   \
+                                 packed, c_in, nt, sa, sb, tpc, gw, acc, stats, X));                                           \
     } while (0)
 #define MOPA_TC_LAUNCH(NA_, LPR_)               \
     do {                                        \
