@@ -62,11 +62,40 @@ def make_batches(a, rank, count):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (every 50 ms, own thread). NVML in-process when
+    pynvml is importable (the same counters nvidia-smi prints, without a second process polling the driver: a looping
+    nvidia-smi stalled single steps by 5-80 ms in young processes); `nvidia-smi -lms` otherwise. BENCH_SAMPLER=smi / none
+    selects the other two behaviours (diagnosis)."""
     FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.samples, self.proc, self.thread = [], None, None
+        self.samples, self.proc, self.thread, self.nvml, self.alive = [], None, None, None, True
+        want = os.environ.get("BENCH_SAMPLER", "nvml")
+        if want == "none":
+            return
+        if want == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                # CUDA_VISIBLE_DEVICES remaps CUDA indices: go through the PCI bus id of the CUDA device
+                props = torch.cuda.get_device_properties(index)
+                handle = None
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    pci = pynvml.nvmlDeviceGetPciInfo(h)
+                    if pci.bus == props.pci_bus_id and pci.domain == props.pci_domain_id:
+                        handle = h
+                if handle is None:
+                    handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+                self.nvml = (pynvml, handle)
+                self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+                self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -76,36 +105,48 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll_nvml(self):
+        nv, h = self.nvml
+        bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+        while self.alive:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.samples.append((time.time(), (sm, self.max_sm, [bool(mask & b) for b in bits])))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append((time.time(), line.strip()))
+            p = [x.strip() for x in line.strip().split(",")]
+            try:
+                self.samples.append((time.time(), (float(p[0]), float(p[1]), [v.lower().startswith("active") for v in p[2:6]])))
+            except (ValueError, IndexError):
+                continue
 
     def wait_ready(self, min_samples=2, timeout=8.0):
-        """nvidia-smi takes a while to start on a multi-GPU box and its first queries hold driver locks for tens of
-        milliseconds (measured at N=2: four 60-80 ms stalls in the first 300 ms): enter the timed region only once the
-        sampler is in its steady 100 ms rhythm."""
+        """Enter the timed region only once the sampler is in its steady rhythm (nvidia-smi takes a while to start on a
+        multi-GPU box and its first queries hold driver locks for tens of milliseconds)."""
         t0 = time.time()
-        while self.proc and len(self.samples) < min_samples and time.time() - t0 < timeout:
+        while (self.proc or self.nvml) and len(self.samples) < min_samples and time.time() - t0 < timeout:
             time.sleep(0.05)
 
     def window(self, t0, t1):
         rows = [s for t, s in self.samples if t0 <= t <= t1] or [s for _, s in self.samples[-3:]]
         sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            p = [x.strip() for x in r.split(",")]
-            try:
-                sm.append(float(p[0]))
-                mx = max(mx, float(p[1]))
-            except (ValueError, IndexError):
-                continue
-            for nme, val in zip(names, p[2:6]):
-                if val.lower().startswith("active"):
+        for clk, clk_max, flags in rows:
+            sm.append(clk)
+            mx = max(mx, clk_max)
+            for nme, on in zip(self.NAMES, flags):
+                if on:
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml else ("nvidia-smi" if self.proc else None)}
 
     def stop(self):
+        self.alive = False
         if self.proc:
             self.proc.terminate()
 
