@@ -545,16 +545,99 @@ __global__ void __launch_bounds__(256) k_dw_generic(Gather gt, const float *__re
     }
 }
 
+// d_weight of a convolution with very few input planes (the network's first layer, 1 -> 16; TF32 mode), where the rows are
+// the only long dimension: dW[k][ci][co] = sum_o x[in(k, o)][ci] dy[o][co] = (Xg^T dY)[k][co] with Xg[o][k] = x[in(k, o)][ci],
+// a (32 x rows) x (rows x n_out) product. mma.sync m16n8k8 takes 8 rows per step: a lane gathers its eight A values
+// (offset m = g, g + 8, g + 16, g + 24; rows t, t + 4) scalar by scalar straight into the fragment layout, dy is read once
+// per row instead of once per offset and row (k_dw_generic: 27 passes over dy, 83 us at 231k rows; this kernel: ~10 us).
+// grid (blocks, 1, n_in); every warp strides over 8-row chunks; warps, then blocks, are summed in index order.
+template <int NT8>
+__global__ void __launch_bounds__(256) k_dw_rows_mma(Gather gt, const float *__restrict__ in, int64_t ld_in,
+                                                     const float *__restrict__ dout, int64_t ld_dout, int n_in,
+                                                     float *__restrict__ partial) {
+    constexpr int n_out = 8 * NT8;
+    __shared__ float red[8][32][n_out + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3, ci = blockIdx.z;
+    const int K = gt.volume;
+    float acc[2][NT8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int j = 0; j < NT8; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mt][j][e] = 0.f;
+    const int64_t n_chunks = (gt.n_out + 7) >> 3, stride = (int64_t)gridDim.x * 8;
+#pragma unroll 2
+    for (int64_t c = (int64_t)blockIdx.x * 8 + warp; c < n_chunks; c += stride) {
+        const int64_t o0 = (c << 3) + t, o1 = o0 + 4;
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int m = 16 * mt + g + 8 * (e & 1);
+                const int64_t o = (e & 2) ? o1 : o0;
+                float x = 0.f;
+                if (m < K && o < gt.n_out) {
+                    const int i = gather_lookup(gt, m, o);
+                    if (i >= 0) x = __ldg(in + (int64_t)i * ld_in + ci);
+                }
+                a[mt][e] = to_tf32(x);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NT8; ++j) {
+            const uint32_t b0 = to_tf32(o0 < gt.n_out ? __ldg(dout + o0 * ld_dout + 8 * j + g) : 0.f);
+            const uint32_t b1 = to_tf32(o1 < gt.n_out ? __ldg(dout + o1 * ld_dout + 8 * j + g) : 0.f);
+            mma_tf32(acc[0][j], a[0], b0, b1);
+            mma_tf32(acc[1][j], a[1], b0, b1);
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int j = 0; j < NT8; ++j) {
+            red[warp][16 * mt + g][8 * j + 2 * t] = acc[mt][j][0];
+            red[warp][16 * mt + g][8 * j + 2 * t + 1] = acc[mt][j][1];
+            red[warp][16 * mt + g + 8][8 * j + 2 * t] = acc[mt][j][2];
+            red[warp][16 * mt + g + 8][8 * j + 2 * t + 1] = acc[mt][j][3];
+        }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < K * n_out; idx += blockDim.x) {
+        const int k = idx / n_out, co = idx - k * n_out;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][k][co];
+        partial[(((int64_t)k * gridDim.x + blockIdx.x) * n_in + ci) * n_out + co] = v;
+    }
+}
+
 // d_weight[k][e] = sum over the k-th group of `per_k` partial slices, in index order (deterministic)
+// grid (element blocks of 32, offsets), block (32 elements, 8 slice groups): thread (x, y) adds slices y, y + 8, ... in order,
+// the 8 sums are combined in y order: a fixed tree, with 8x shorter load chains than one thread per element.
 __global__ void __launch_bounds__(256) k_dw_reduce(const float *__restrict__ partial, int per_k, int64_t mat,
-                                                   float *__restrict__ dw, int64_t total) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int64_t k = idx / mat, e = idx - k * mat;
-    const float *p = partial + k * per_k * mat + e;
-    float s = 0.f;
-    for (int c = 0; c < per_k; ++c) s += p[(int64_t)c * mat];
-    dw[idx] = s;
+                                                   float *__restrict__ dw) {
+    __shared__ float red[8][33];
+    const int k = blockIdx.y;
+    const int64_t e = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    float s0 = 0.f, s1 = 0.f;
+    if (e < mat) {
+        const float *p = partial + (int64_t)k * per_k * mat + e;
+        int c = threadIdx.y;
+        for (; c + 8 < per_k; c += 16) {
+            s0 += p[(int64_t)c * mat];
+            s1 += p[(int64_t)(c + 8) * mat];
+        }
+        if (c < per_k) s0 += p[(int64_t)c * mat];
+    }
+    red[threadIdx.y][threadIdx.x] = s0 + s1;
+    __syncthreads();
+    if (threadIdx.y == 0 && e < mat) {
+        float s = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x];
+        dw[(int64_t)k * mat + e] = s;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host dispatch
@@ -684,8 +767,20 @@ static DwPlan dw_plan(int volume, int n_in, int n_out, int64_t n_rows) {
     return p;
 }
 
+// blocks of k_dw_rows_mma: >= 6 chunks of 8 rows per warp, at most two blocks per SM of the reference device (a function of
+// the row count only: the summation tree must not depend on the caller's workspace or on the device at hand)
+static int dw_rows_blocks(int64_t n_rows) {
+    int64_t b = ceil_div(ceil_div(n_rows > 0 ? n_rows : 1, 8), 8 * 6);
+    return (int)(b < 1 ? 1 : (b > 2 * kNumSMs ? 2 * kNumSMs : b));
+}
+static bool dw_rows_supported(int volume, int n_in, int n_out) { return n_in <= 4 && (n_out == 16 || n_out == 32) && volume <= 32; }
+
 size_t dw_workspace_bytes(int volume, int n_in, int n_out, int64_t n_rows) {
     size_t b = dw_plan(volume, n_in, n_out, n_rows).partial_bytes;
+    if (dw_rows_supported(volume, n_in, n_out)) {
+        const size_t t = (size_t)volume * dw_rows_blocks(n_rows) * n_in * n_out * 4;
+        if (t > b) b = t;
+    }
     if (dw_tc_supported(n_in, n_out)) {
         const size_t t = dw_tc_workspace_bytes(volume, n_in, n_out, n_rows);
         if (t > b) b = t;
@@ -747,6 +842,15 @@ int conv_dweight(const Gather &gt, const float *in, int64_t ld_in, const float *
             default: MOPA_FAIL("d_weight: channel counts too large");
         }
 #undef MOPA_DW
+    } else if (precision == MOPA_SCN_PREC_TF32 && dw_rows_supported(gt.volume, n_in, n_out)) {
+        // few input planes (the first layer): rows as the GEMM's K dimension
+        const int blocks = dw_rows_blocks(gt.n_out);
+        MOPA_CHECK(workspace_bytes >= (size_t)gt.volume * blocks * mat * 4, "backward workspace too small");
+        p.per_k = blocks;
+        dim3 grid(blocks, 1, n_in);
+        if (n_out == 16) k_dw_rows_mma<2><<<grid, 256, 0, s>>>(gt, in, ld_in, dout, ld_dout, n_in, partial);
+        else k_dw_rows_mma<4><<<grid, 256, 0, s>>>(gt, in, ld_in, dout, ld_dout, n_in, partial);
+        MOPA_LAUNCHED();
     } else {
         p.WK = 1;
         p.per_k = p.nchunks;
@@ -754,8 +858,7 @@ int conv_dweight(const Gather &gt, const float *in, int64_t ld_in, const float *
         k_dw_generic<<<grid, 256, 0, s>>>(gt, in, ld_in, dout, ld_dout, n_in, n_out, p.rows_per_chunk, partial);
         MOPA_LAUNCHED();
     }
-    const int64_t total = (int64_t)gt.volume * mat;
-    k_dw_reduce<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(partial, p.per_k, mat, dw, total);
+    k_dw_reduce<<<dim3((unsigned)ceil_div(mat, 32), gt.volume), dim3(32, 8), 0, s>>>(partial, p.per_k, mat, dw);
     MOPA_LAUNCHED();
     return 0;
 }
