@@ -537,6 +537,17 @@ static int64_t bn_fused_min_elems() {
     }();
     return v;
 }
+// ... and up to this many elements (default 0: never). Small tensors are the case where the cooperative kernel cannot hurt
+// the other stream (its grid is a handful of blocks) and where the second launch + the fence / counter chain of the
+// two-kernel path cost most relative to the work: MOPA_SCN_BN_FUSED_MAX=<elements>.
+static int64_t bn_fused_max_elems() {
+    static const int64_t v = [] {
+        const char *e = getenv("MOPA_SCN_BN_FUSED_MAX");
+        return e ? (int64_t)atoll(e) : (int64_t)0;
+    }();
+    return v;
+}
+static bool bn_use_fused(int64_t elems) { return elems >= bn_fused_min_elems() || elems <= bn_fused_max_elems(); }
 template <int VEC, bool BWD>
 static int launch_bn_fused(const BnShapeArgs &A, cudaStream_t s) {
     const int tx = A.planes / VEC;
@@ -653,7 +664,7 @@ int bn_forward(const float *in, int64_t ld_in, float *out, int64_t ld_out, float
         prof_end(prof, s);
         return 0;
     }
-    if (train && sh.vec == 4 && bn_fused_enabled() && n_active * planes >= bn_fused_min_elems()) {
+    if (train && sh.vec == 4 && bn_fused_enabled() && bn_use_fused(n_active * planes)) {
         const BnShapeArgs A{in, ld_in, nullptr, 0, out, ld_out, n_active, planes, ws, nullptr, nullptr, weight, bias, leakiness,
                             1, eps, momentum, save_mean, save_invstd, running_mean, running_var, nullptr, nullptr, 0};
         const int rc = launch_bn_fused<4, false>(A, s);
@@ -710,7 +721,7 @@ int bn_backward(const float *in, int64_t ld_in, float *d_in, int64_t ld_din, con
         prof_end(prof, s);
         return 0;
     }
-    if (sh.vec == 4 && bn_fused_enabled() && n_active * planes >= bn_fused_min_elems()) {
+    if (sh.vec == 4 && bn_fused_enabled() && bn_use_fused(n_active * planes)) {
         const BnShapeArgs A{in, ld_in, d_out, ld_dout, d_in, ld_din, n_active, planes, ws, save_mean, save_invstd, weight, bias,
                             leakiness, train, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, d_weight, d_bias, accumulate};
         const int rc = launch_bn_fused<4, true>(A, s);

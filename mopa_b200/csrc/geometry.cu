@@ -75,6 +75,7 @@ int meta_alloc(mopa_scn_metadata *m, void **p, size_t bytes, cudaStream_t s) {
     if (bytes == 0) bytes = 16;
     MOPA_CUDA(cudaMallocAsync(p, bytes, s));
     m->allocs.push_back(*p);
+    m->alloc_stream = s;
     return 0;
 }
 
@@ -787,6 +788,35 @@ int mopa_scn_Profile_read(mopa_scn_profile_record *out, int64_t max_records) {
     return 0;
 }
 
+struct Parked {
+    int device;
+    cudaEvent_t done;
+    cudaStream_t stream;
+    std::vector<void *> ptrs;
+};
+static std::mutex g_park_mu;
+static std::vector<Parked> g_parked;
+// Also the throttle of a loop that never synchronises: with the geometry on its own stream nothing else stops the host
+// from queueing step after step (measured: the pool kept growing and single steps stalled for 100-350 ms). More than
+// kMaxParked forwards whose memory is still in use -> wait for the oldest: the host stays about one step ahead.
+constexpr int kMaxParked = 1;
+static void reap_parked(int device) {  // current device == device
+    std::lock_guard<std::mutex> lk(g_park_mu);
+    int mine = 0;
+    for (const Parked &e : g_parked) mine += e.device == device;
+    for (size_t i = 0; i < g_parked.size();) {
+        Parked &e = g_parked[i];
+        if (e.device != device) { ++i; continue; }
+        if (mine > kMaxParked) cudaEventSynchronize(e.done);  // (entries are in order of deletion: this is the oldest)
+        if (cudaEventQuery(e.done) != cudaSuccess) { ++i; continue; }
+        for (void *p : e.ptrs) cudaFreeAsync(p, e.stream);
+        cudaEventDestroy(e.done);
+        g_parked.erase(g_parked.begin() + (long)i);
+        --mine;
+    }
+    cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error
+}
+
 mopa_scn_metadata *mopa_scn_Metadata_new(int dimension, int device) {
     if (dimension != 3) {
         fail(__FILE__, __LINE__, "only dimension 3 is supported (scn_unet.py: DIMENSION = 3)");
@@ -801,6 +831,7 @@ mopa_scn_metadata *mopa_scn_Metadata_new(int dimension, int device) {
         uint64_t thr = UINT64_MAX;  // keep freed blocks cached: per-forward scratch is re-used, not re-mapped
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    reap_parked(device);
     auto *m = new mopa_scn_metadata();
     m->device = device;
     m->pinned = pin_get();
@@ -817,7 +848,27 @@ void mopa_scn_Metadata_delete(mopa_scn_metadata *m) {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(m->device);
-    for (void *p : m->allocs) cudaFreeAsync(p, m->last_stream);
+    // Blocks allocated on another stream than the one that used them last (compiled networks: the geometry stream) are
+    // parked with an event of the last user and freed ON THEIR ALLOCATION STREAM once that event has completed (reap_parked,
+    // called when the next Metadata is created): the pool then recycles them in plain stream order and nothing ever waits.
+    // Freed on the compute stream instead, the geometry stream's next allocations (issued while the compute stream is a
+    // step behind) found only blocks whose release was still pending and the pool grew by fresh device memory (rare
+    // 30-90 ms stalls); made to wait for the compute stream, the geometry of step i+1 no longer overlapped step i.
+    bool parked = false;
+    if (!m->allocs.empty() && m->alloc_stream != m->last_stream) {
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+            if (cudaEventRecord(ev, m->last_stream) == cudaSuccess) {
+                std::lock_guard<std::mutex> lk(g_park_mu);
+                g_parked.push_back(Parked{m->device, ev, m->alloc_stream, std::move(m->allocs)});
+                parked = true;
+            } else {
+                cudaEventDestroy(ev);
+            }
+        }
+    }
+    if (!parked)
+        for (void *p : m->allocs) cudaFreeAsync(p, m->last_stream);
     if (m->geom_done) cudaEventDestroy(m->geom_done);
     cudaSetDevice(prev);
     pin_put(m->pinned);

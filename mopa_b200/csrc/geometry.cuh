@@ -47,6 +47,7 @@ struct mopa_scn_metadata {
     int32_t *csr_rows = nullptr;  // [n_points] ascending inside a voxel
     std::vector<void *> allocs;
     cudaStream_t last_stream = nullptr;
+    cudaStream_t alloc_stream = nullptr;  // stream of the (last) meta_alloc; see Metadata_delete
     int32_t *pinned = nullptr;  // small host staging block for counts
     cudaEvent_t geom_done = nullptr;  // recorded on the geometry stream when grids/tables are complete
     // device-side site counts: cnt_dev[l] = V of level l, cnt_dev[31] = coordinate error flag. Levels are hashed back to
