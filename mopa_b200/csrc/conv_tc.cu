@@ -11,23 +11,25 @@
 //
 // What round 1 / the first half of round 2 measured (profiles/r01_*, r02_conv_tc_history.txt): with the rulebook as a
 // dense (offset, row) -> row table, the gather warps spend ~130 instructions per (warp, offset) on ballots, shuffles and
-// bookkeeping for ~4 live rows, 16 such warps per SM: the kernel was INSTRUCTION-ISSUE bound (0.21 of the HBM roofline,
-// DRAM 6-8 % busy, tensor pipe 4-14 %). Cutting the LDGSTS count 3-6x by compacting inside the warp changed nothing.
-// So the compaction moved out of this kernel: geometry.cu::k_tile_lists_batch builds, once per level and shared by the six
-// convolution passes that use the level, the rulebook in the form this kernel consumes: per (tile, offset) a compact
-// list of (input row, tile row) pairs and the 128-bit row mask. Here
-//   warps 0-7  gather : 4 per tile. Live offsets of the CTA are dealt round-robin to the tile's 4 warps; ONE warp
-//                       fills a whole stage: it loads 32 list entries with one coalesced LDG (the next step's entries
-//                       are prefetched), and per pass copies 32 / LPR rows with one LDGSTS (LPR lanes x 16 bytes per
-//                       row, cp.async straight into the swizzled stage). Completion arrives on the stage's mbarrier
-//                       asynchronously (cp.async.mbarrier.arrive.noinc): a warp never waits for data.
+// bookkeeping for ~4 live rows. Moving that out of the kernel (geometry.cu::k_tile_lists_batch builds, once per level and
+// shared by the six convolution passes that use the level, per (tile, offset) a compact list of (input row, tile row) pairs
+// and the 128-bit row mask) cut the instruction count ~4x and did NOT change the time: a stage-step is a ~2200-cycle chain
+// (copies issued -> data landed -> MMAs issued -> commit -> stage free) and what bounds the kernel is how many such chains
+// an SM keeps in flight (profiles/r02_tc_timeline.txt). Hence the roles:
+//   warps 0-7  gather : 4 per tile, in GW groups; a group fills every GW-th stage-step of its tile, so a stage is always
+//                       filled by the same warps (mbarrier parity waits cannot tell phases two apart). A warp loads 32
+//                       list entries with one coalesced LDG (the next step's entries are prefetched) and per pass copies
+//                       32 / LPR rows with one LDGSTS (LPR lanes x 16 bytes per row, cp.async straight into the swizzled
+//                       stage). Completion arrives on the stage's mbarrier asynchronously (cp.async.mbarrier.arrive.noinc).
 //   warp  8    weights: one lane streams W[k] chunks of the live offsets (pre-packed N x K K-major) by TMA bulk copy.
-//   warps 9,10 MMA    : one issuer warp per tile: elected lane issues the masked tcgen05.mma's, commits stage releases.
-//   epilogue          : gather warp (tile mt, quarter wq) reads TMEM lanes [32 wq, +32) and writes each output row once
-//                       (optionally accumulating), and reduces per-column sum / sum of squares for the BatchNorm that
-//                       follows (shuffle transpose-reduce, one fp64 atomic per column and CTA).
-// Offsets with no rule in any tile of the CTA are skipped by all three roles (same 27-bit live set, from the masks).
-// Summation order is fixed (live k ascending, chunks ascending, hardware order inside an MMA): outputs are deterministic.
+//   warps 9..  MMA    : ACC issuer warps per tile, each with its OWN TMEM accumulator set and every ACC-th stage-step:
+//                       elected lane issues the masked tcgen05.mma's and commits the stage releases.
+//   epilogue          : gather warp (tile mt, quarter wq) reads TMEM lanes [32 wq, +32), adds the ACC sets, writes each
+//                       output row once (optionally accumulating), and reduces two per-column sums for the BatchNorm next
+//                       to the convolution (forward: sum x, sum x^2; optional d_input variant: the backward sums).
+// Offsets with no rule in any tile of the CTA are skipped by all three roles (same 27-bit live set, from the masks). On the
+// small levels the live offsets of a tile are split over several CTAs (TcExtra::split). Summation order is fixed: outputs
+// are deterministic run to run.
 #include <stdlib.h>
 
 #include <mutex>

@@ -22,6 +22,18 @@ from . import modules as M
 OP_SUBM, OP_CONV, OP_DECONV, OP_BN = 1, 2, 3, 4
 
 
+
+def _arena_bytes(n):
+    """Arena sizes rounded up to 1/16 of their power of two: consecutive batches differ by a few per cent in size, and
+    torch's caching allocator only reuses a cached block for a request of (nearly) the same size; exact sizes made it
+    cudaMalloc a fresh multi-GB segment per distinct batch size and per step in flight (visible as 50 ms - 1 s stalls)."""
+    n = int(n)
+    if n < (1 << 20):
+        return max(n, 1)
+    q = 1 << (n.bit_length() - 5)
+    return (n + q - 1) // q * q
+
+
 class _Unsupported(Exception):
     pass
 
@@ -227,8 +239,8 @@ class _ProgramFunction(Function):
             _lib.check(L.mopa_scn_Program_prepare(handle, meta._h, coords.data_ptr(), n, ncols, where, prec, stream, n_active,
                                                   sizes))
             meta.n_points = n
-            act = torch.empty(sizes[0], dtype=torch.uint8, device=dev)
-            scratch = torch.empty(sizes[2], dtype=torch.uint8, device=dev)
+            act = torch.empty(_arena_bytes(sizes[0]), dtype=torch.uint8, device=dev)
+            scratch = torch.empty(_arena_bytes(sizes[2]), dtype=torch.uint8, device=dev)
             out = torch.empty(n, prog.bufs[prog.out_buf][1], dtype=torch.float32, device=dev)
             tensors = prog.tensors()
             params = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
@@ -279,8 +291,8 @@ class _ProgramFunction(Function):
                 grads.append(g)
             params = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() if t is not None else None for t in tensors])
             pgrads = (ctypes.c_void_p * len(tensors))(*ptrs)
-            grad_arena = torch.empty(ctx.sizes[0], dtype=torch.uint8, device=dev)
-            scratch = torch.empty(ctx.sizes[1], dtype=torch.uint8, device=dev)
+            grad_arena = torch.empty(_arena_bytes(ctx.sizes[0]), dtype=torch.uint8, device=dev)
+            scratch = torch.empty(_arena_bytes(ctx.sizes[1]), dtype=torch.uint8, device=dev)
             d_feats = torch.zeros(ctx.n_rows, prog.in_planes, dtype=torch.float32, device=dev) if need[3] else None
             _lib.check(L.mopa_scn_Program_backward(
                 prog.handle, meta._h, params, pgrads, 1 if ctx.train else 0, ctx.prec, ctx.act.data_ptr(),

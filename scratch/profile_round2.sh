@@ -7,7 +7,9 @@ if ! grep -q "xm operators ok" $O/${TG}_smoke.log; then echo "SMOKE FAILED - sto
 $T 900 python -m pytest tests -m gpu -q 2>&1 | tail -12 > $O/${TG}_tests.log; tail -6 $O/${TG}_tests.log
 $T 300 python tools/grad_error_table.py --sensor nuscenes --out $O/${TG}_grad_errors > $O/${TG}_grad_errors.log 2>&1; tail -5 $O/${TG}_grad_errors.log
 $T 300 python tools/grad_error_table.py --sensor kitti --out $O/${TG}_grad_errors_kitti > /dev/null 2>&1
-$T 400 python bench.py > $O/${TG}_bench.json 2> $O/${TG}_bench.err; cut -c1-200 $O/${TG}_bench.json; tail -2 $O/${TG}_bench.err
+$T 400 python bench.py > $O/${TG}_bench.json 2> $O/${TG}_bench.err; python scratch/print_bench.py $O/${TG}_bench.json; tail -2 $O/${TG}_bench.err
+$T 200 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/${TG}_bench_k20.json 2>> $O/${TG}_bench.err; python scratch/print_bench.py $O/${TG}_bench_k20.json
+$T 200 python tools/train_ab.py --steps 200 > $O/${TG}_train_ab.txt 2>> $O/${TG}_bench.err; tail -8 $O/${TG}_train_ab.txt
 $T 300 python tools/layer_table.py --out $O/${TG}_layers.json > $O/${TG}_layers.log 2>&1; tail -7 $O/${TG}_layers.log
 $T 900 python tools/sweep.py --out $O/${TG}_sweep.json > $O/${TG}_sweep.log 2>&1; cat $O/${TG}_sweep.log
 B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-roofline --no-fp32"
