@@ -690,7 +690,12 @@ int conv_apply_tc(const Gather &gt, const float *in, int64_t ld_in, float *out, 
         acc = want_acc >= 4 ? 4 : (want_acc >= 2 ? 2 : 1);
         while (acc > 1 && (tc_tmem_cols(nt, tpc * acc) > (two ? 256 : 512) || 32 * (9 + tpc * acc) > (two ? 13 * 32 : kTcMaxThreads))) acc >>= 1;
         sb = want_sb >= 4 ? 4 : 2;
-        while (sb > 2 && (size_t)sb * na * nt * 128 > (size_t)(tpc == 2 ? 64 : 32 * na) * 1024) sb -= 2;
+        // weight ring budget: a CTA that has the SM to itself (the small levels) may spend up to 120 KB on it, so that wide
+        // layers (28 KB per weight stage) still get two stages per issuer and the TMA loads run one step ahead
+        // (level-5 convolutions 39 -> 35, 47 -> 41, 36 -> 30 us); shared SMs keep the ring small
+        static const int bcap_kb = env_int("MOPA_TC_BCAP_KB", 120);
+        const size_t bcap = !two ? (size_t)bcap_kb * 1024 : (size_t)(tpc == 2 ? 64 : 32 * na) * 1024;
+        while (sb > 2 && (size_t)sb * na * nt * 128 > bcap) sb -= 2;
         if (acc > sb) acc = sb;
         const int unit = tpc * acc;  // sa must be a multiple of it
         sa = want_sa >= unit && want_sa <= kTcMaxSA ? want_sa : kTcMaxSA;
