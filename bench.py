@@ -287,7 +287,8 @@ def roofline_pass(net, batches_dev, steps, peaks):
             "launches_timed": n, "avg_launch_us": 1e6 * t / max(n, 1), "algorithmic_bytes_per_launch": b / max(n, 1),
             "tflops_useful": fl / t / 1e12 if t > 0 else 0.0,
             "per_class": {k: {"ms_per_step": 1e3 * v[1] / max(steps, 1), "gbs": v[0] / v[1] / 1e9 if v[1] else 0.0,
-                              "frac": v[0] / v[1] / 1e9 / peak if v[1] else 0.0, "launches": v[2]} for k, v in cls.items()}}
+                              "frac": v[0] / v[1] / 1e9 / peak if v[1] else 0.0, "launches": v[2]} for k, v in cls.items()},
+            "algorithmic_bytes_per_step": sum(v[0] for v in cls.values()) / max(steps, 1)}
 
 
 def geometry_pass(net, batches_dev, peaks, reps=10):
@@ -516,6 +517,11 @@ def run_ours(a):
             "all_reduce_us_median": ar_us,
             "fp32_ms_per_step": (1e3 * fp32["sec"] / max(5, min(20, a.steps // 5))) if fp32 else None,
             "gpu_launches": res["launches"], "clocks": clocks, "roofline": roof, "geometry": geo, "cpu_baseline": cpu}
+        if roof:  # the whole step against the same peak: all five classes' algorithmic bytes / the timed step
+            gbs = roof["algorithmic_bytes_per_step"] / (line["ms_per_step"] * 1e-3) / 1e9
+            roof["whole_step"] = {"achieved": gbs, "unit": "GB/s", "frac": gbs / roof["peak"],
+                                  "note": "conv forward / d_input / d_weight + BatchNorm forward / backward bytes of one step "
+                                          "(SURVEY 8(d)) over ms_per_step; geometry and I/O layers not counted"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -175,3 +175,23 @@ def test_compiled_for_caches_and_respects_eager_switch(monkeypatch):
     assert compiler._grad_view_of(params[0]) is views[params[0]] and compiler._grad_view_of(params[5]) is None
     compiler.unregister_grad_views(params[:3])
     assert compiler._grad_view_of(params[0]) is None
+
+
+def test_arena_sizes_fall_into_coarse_classes():
+    """Arena sizes are rounded up to 1/16 of their power of two (compiler._arena_bytes): batches a few per cent apart share a
+    size class, the request is never below the real size and never more than 1/16 above it."""
+    from mopa_b200.scn.compiler import _arena_bytes
+    for n in (1, 1000, (1 << 20) - 1, (1 << 20) + 1, 123456789, 1000000000, 1010000000, 6100000000):
+        r = _arena_bytes(n)
+        assert r >= n and r <= n + max(1, n // 16) + 1
+    assert _arena_bytes(1000000000) == _arena_bytes(1005000000)
+
+
+def test_host_coordinates_are_passed_as_host_pointers():
+    """coords_on_device of the C ABI: 0 for host tensors whatever attributes they carry (the ready-event shortcut is for
+    device tensors only)."""
+    import torch
+    from mopa_b200.scn.functional import _coords_where
+    c = torch.zeros(4, 4, dtype=torch.int64)
+    c._mopa_ready = object()
+    assert _coords_where(c) == 0
