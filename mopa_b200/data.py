@@ -31,12 +31,28 @@ def mark_ready(tensor):
     return tensor
 
 
+def map_tensors(obj, fn):
+    """Apply fn to every tensor inside nested dicts / lists / tuples (MoPA's collate output: a dict with 'x': [coords,
+    feats], 'seg_label', 'img', 'img_indices': [ndarray, ...], ... -- mopa/data/collate.py:170-260); everything else is
+    passed through untouched."""
+    if torch.is_tensor(obj):
+        return fn(obj)
+    if isinstance(obj, dict):
+        return {k: map_tensors(v, fn) for k, v in obj.items()}
+    if isinstance(obj, tuple):
+        return tuple(map_tensors(v, fn) for v in obj)
+    if isinstance(obj, list):
+        return [map_tensors(v, fn) for v in obj]
+    return obj
+
+
 class DevicePrefetcher:
     """Iterate over host batches, handing out device copies `depth` batches ahead.
 
-    batches: iterable of `[coords, feats]` (coords int64 (N, 3|4), feats float32 (N, C)); tensors that are not pinned
-    are pinned first (an extra host copy: pin them in the DataLoader, `pin_memory=True`, to avoid it).
-    The yielded `[coords_dev, feats_dev]` goes straight into `UNetSCN.forward` / `scn.InputLayer`.
+    batches: iterable of `[coords, feats]` (coords int64 (N, 3|4), feats float32 (N, C)) or of any nesting of dicts /
+    lists / tuples holding tensors (a MoPA `data_batch`): every tensor is copied, everything else is passed through.
+    Tensors that are not pinned are pinned first (an extra host copy: pin them in the DataLoader, `pin_memory=True`, to
+    avoid it). The yielded `[coords_dev, feats_dev]` / `data_batch['x']` goes straight into `UNetSCN.forward`.
     """
 
     def __init__(self, batches, device=None, depth=2):
@@ -61,12 +77,14 @@ class DevicePrefetcher:
             self._done = True
             return
         with torch.cuda.stream(self._stream):
-            out = [self._pin(t).to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in batch]
+            out = map_tensors(batch, lambda t: self._pin(t).to(self.device, non_blocking=True))
             ready = torch.cuda.Event()
             ready.record(self._stream)
-        for t in out:
-            if torch.is_tensor(t):
-                t._mopa_ready = ready
+
+        def tag(t):
+            t._mopa_ready = ready
+            return t
+        map_tensors(out, tag)
         self._queue.append((out, ready))
 
     def __iter__(self):
@@ -80,9 +98,11 @@ class DevicePrefetcher:
         out, ready = self._queue.popleft()
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ready)
-        for t in out:
-            if torch.is_tensor(t):
-                t.record_stream(cur)  # allocated on the copy stream, consumed on the caller's
+
+        def used_on_caller(t):
+            t.record_stream(cur)  # allocated on the copy stream, consumed on the caller's
+            return t
+        map_tensors(out, used_on_caller)
         self._issue()  # keep `depth` copies in flight while the caller works on this batch
         return out
 

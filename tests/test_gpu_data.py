@@ -96,3 +96,19 @@ def test_bn_backward_sums_from_the_conv_epilogue_match_the_two_kernel_path(cuda)
             os.environ.pop("MOPA_SCN_BNBWD_FUSION", None)
         else:
             os.environ["MOPA_SCN_BNBWD_FUSION"] = old
+
+
+def test_prefetcher_moves_a_nested_data_batch(cuda):
+    """A MoPA-style data_batch (dict with 'x': [coords, feats], labels, non-tensor fields): tensors arrive on the device
+    carrying the copy's event, everything else is passed through; the coordinates are accepted as complete."""
+    import numpy as np
+    from mopa_b200.data import DevicePrefetcher
+    from mopa_b200.scn.functional import _coords_where
+    c, f = synth.make_batch(1, "nuscenes", 2, n_azimuth=80)
+    batch = {"x": [torch.from_numpy(c), torch.from_numpy(f)], "seg_label": torch.zeros(c.shape[0], dtype=torch.int64),
+             "img_indices": [np.zeros((c.shape[0], 2), np.int64)], "name": "scan-0"}
+    (out,) = list(DevicePrefetcher(iter([batch])))
+    assert out["x"][0].is_cuda and out["x"][1].is_cuda and out["seg_label"].is_cuda
+    assert out["name"] == "scan-0" and out["img_indices"][0] is batch["img_indices"][0]
+    assert torch.equal(out["x"][0].cpu(), batch["x"][0])
+    assert _coords_where(out["x"][0]) == 2 and _coords_where(out["x"][0].clone()) == 1

@@ -195,3 +195,17 @@ def test_host_coordinates_are_passed_as_host_pointers():
     c = torch.zeros(4, 4, dtype=torch.int64)
     c._mopa_ready = object()
     assert _coords_where(c) == 0
+
+
+def test_map_tensors_walks_a_mopa_data_batch():
+    """mopa_b200.data.map_tensors: every tensor of a nested batch (dict / list / tuple, the shape of MoPA's collate output)
+    is transformed, everything else is passed through, the structure is preserved."""
+    import numpy as np
+    import torch
+    from mopa_b200.data import map_tensors
+    batch = {"x": [torch.zeros(3, 4, dtype=torch.int64), torch.ones(3, 1)], "seg_label": torch.arange(3),
+             "img_indices": [np.zeros((3, 2), np.int64)], "id": ("a", 7), "nested": {"t": (torch.ones(2),)}}
+    out = map_tensors(batch, lambda t: t + 1)
+    assert set(out) == set(batch) and isinstance(out["x"], list) and isinstance(out["nested"]["t"], tuple)
+    assert torch.equal(out["x"][0], batch["x"][0] + 1) and torch.equal(out["nested"]["t"][0], torch.full((2,), 2.0))
+    assert out["img_indices"][0] is batch["img_indices"][0] and out["id"] == ("a", 7)
