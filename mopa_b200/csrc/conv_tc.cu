@@ -57,6 +57,8 @@ __host__ __device__ inline int tc_tmem_cols(int nt, int tpc = 2) {  // power of 
 
 // packed[k][chunk][NT rows x 128 bytes, SWIZZLE_128B]: B operand (N x K, K-major) of one pipeline step.
 // element (n, c) of a chunk = W'[ci = 32 chunk + c][co = n], rounded to TF32 (zero for ci >= c_in).
+// c_in == 16 (half a swizzle row per offset): tile p holds a PAIR of offsets, channels [0, 16) = offset 2p, [16, 32) = offset
+// 2p + 1 (zero past the last offset); tiles ceil(K / 2) .. K - 1 are unused. The kernel then runs one stage-step per pair.
 __device__ __forceinline__ void tc_pack_element(const float *__restrict__ w, int volume, int n_in0, int n_out0, int transpose,
                                                 int flip, float *__restrict__ packed, int64_t idx) {
     const int c_in = transpose ? n_out0 : n_in0, nt = transpose ? n_in0 : n_out0;
@@ -69,8 +71,14 @@ __device__ __forceinline__ void tc_pack_element(const float *__restrict__ w, int
     // r = float index inside the swizzled tile: row n = r / 32, physical 16-byte piece pp = (r % 32) / 4
     const int n = (int)(r >> 5), pp = (int)(r & 31) >> 2, e = (int)(r & 3);
     const int c = ((pp ^ (n & 7)) << 2) + e;  // logical channel inside the chunk
-    const int ci = chunk * kTcChunk + c, co = n;
-    const int ks = flip ? volume - 1 - k : k;
+    int ci = chunk * kTcChunk + c, kk = k;
+    const int co = n;
+    if (c_in == 16) {  // paired offsets
+        kk = 2 * k + (c >> 4);
+        ci = c & 15;
+        if (kk >= volume) ci = c_in;  // -> zero
+    }
+    const int ks = flip ? volume - 1 - kk : kk;
     float v = 0.f;
     if (ci < c_in) v = transpose ? w[((int64_t)ks * n_in0 + co) * n_out0 + ci] : w[((int64_t)ks * n_in0 + ci) * n_out0 + co];
     packed[idx] = __uint_as_float(to_tf32(v));
@@ -157,6 +165,10 @@ __global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 
     float *cst = reinterpret_cast<float *>(smem + L.cst);
     const int S = X.split;
 
+    // LPR == 4 is the 16-input-channel instantiation: a row is half a swizzle row, so a stage-step carries TWO offsets
+    // (2u in bytes [0, 64) of the rows, 2u + 1 in [64, 128)), each multiplied under its own row mask: half as many trips
+    // through the ~2200-cycle hand-off chain for the layers of the largest level.
+    constexpr bool PAIR = LPR == 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     TC_STAMP(tid == 0 && blockIdx.x == gridDim.x / 2, 7, 0);
     const int K = gt.volume;                                // 8 or 27: one lane per offset below
@@ -182,6 +194,13 @@ __global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 
         if (n_mt == 2) mk1 = __ldg(gt.tm + (tile0 + 1) * K + lane);
     }
     uint32_t liveset = __ballot_sync(0xffffffffu, (mk0.x | mk0.y | mk0.z | mk0.w | mk1.x | mk1.y | mk1.z | mk1.w) != 0u);
+    if (PAIR) {  // from here on a bit of the live set is a UNIT of the pipeline: the pair of offsets (2u, 2u + 1)
+        const uint32_t t = (liveset | (liveset >> 1)) & 0x15555555u;
+        uint32_t units = 0;
+#pragma unroll
+        for (int u = 0; u < 14; ++u) units |= ((t >> (2 * u)) & 1u) << u;
+        liveset = units;
+    }
     if (S > 1) {  // this CTA's share: live offsets number blockIdx.y, blockIdx.y + S, ...
         uint32_t mine = 0;
         int r = 0;
@@ -250,28 +269,34 @@ __global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 
             c += GW;
             while (r && c >= nchunk) { c -= nchunk; r &= r - 1; }
         };
-        int en[kTcAhead], en1[kTcAhead];
+        int en[kTcAhead], en1[kTcAhead], eb[kTcAhead], eb1[kTcAhead];  // (eb*: the second offset of a pair)
         uint32_t rest_p = rest;  // prefetch cursor
         int ch_p = ch;
-        auto prefetch = [&](int &e, int &e1) {
+        auto prefetch = [&](int &e, int &e1, int &f, int &f1) {
             if (!rest_p) return;
-            const int kn = __ffs(rest_p) - 1;
+            const int un = __ffs(rest_p) - 1, kn = PAIR ? 2 * un : un;
             const int32_t *src = tl_tile + (kn << 7) + lane;
             e = __ldg(src);
             if (__shfl_sync(0xffffffffu, cnt, kn) > 32) e1 = __ldg(src + 32);
+            if (PAIR) {
+                const int nb2 = __shfl_sync(0xffffffffu, cnt, kn + 1);  // (lanes >= K hold 0)
+                if (nb2 > 0) f = __ldg(src + 128);
+                if (nb2 > 32) f1 = __ldg(src + 160);
+            }
             advance(rest_p, ch_p);
         };
 #pragma unroll
-        for (int u = 0; u < kTcAhead; ++u) { en[u] = en1[u] = 0; prefetch(en[u], en1[u]); }
+        for (int u = 0; u < kTcAhead; ++u) { en[u] = en1[u] = eb[u] = eb1[u] = 0; prefetch(en[u], en1[u], eb[u], eb1[u]); }
         int tstep = 0;  // trace builds only
         while (rest) {
 #pragma unroll
           for (int u = 0; u < kTcAhead; ++u) {
             if (!rest) break;  // warp-uniform
-            const int k = __ffs(rest) - 1;
+            const int k = PAIR ? 2 * (__ffs(rest) - 1) : __ffs(rest) - 1;
             const int n = __shfl_sync(0xffffffffu, cnt, k);  // rules of my tile at this offset (0: only the other tile has some)
-            const int e0 = en[u], e1 = en1[u];
-            prefetch(en[u], en1[u]);
+            const int n2 = PAIR ? __shfl_sync(0xffffffffu, cnt, k + 1) : 0;  // ... at the pair's second offset
+            const int e0 = en[u], e1 = en1[u], f0 = eb[u], f1 = eb1[u];
+            prefetch(en[u], en1[u], eb[u], eb1[u]);
             const int cho = ch * (chw * 4);                  // byte offset of this step's channels in a feature row
             const int left = c_in - ch * chw;
             const bool has0 = cl < min(kTcChunk, left) / 4;                                 // this lane's piece exists in atom 0
@@ -282,23 +307,30 @@ __global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 
             TC_STAMP(warp == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 1, tstep);
             const uint32_t tile_a = sA_a + st * a_stage;
             // one block of up to 32 list entries (held one per lane in `e`): pass j copies rows j RPP .. j RPP + RPP - 1
-            auto copy_pass = [&](int e, int nb, int j) {
+            // `half`: 0, or 4 for the second offset of a pair (16-byte pieces 4..7 of the row)
+            auto copy_pass = [&](int e, int nb, int j, uint32_t half) {
                 const int idx = j * RPP + rl;
                 const int ent = __shfl_sync(0xffffffffu, e, idx);
                 const uint32_t r = (uint32_t)ent >> kTileRowShift;
                 const char *src = in_c + (uint64_t)((uint32_t)ent & ((1u << kTileRowShift) - 1u)) * (uint64_t)ldb + cho;
-                const uint32_t dst = tile_a + r * 128u + (((uint32_t)cl ^ (r & 7u)) << 4);
+                const uint32_t dst = tile_a + r * 128u + ((((uint32_t)cl + half) ^ (r & 7u)) << 4);
                 const bool ok = idx < nb;
                 cp_async16_guard_s(dst, src, (ok && has0) ? 1u : 0u);
                 if (NA == 2) cp_async16_guard_s(dst + kTcAStage, src + 128, (ok && has1) ? 1u : 0u);
             };
-            auto copy_block = [&](int e, int nb) {  // nb >= 1, warp-uniform; this warp's passes of the block: mi, mi + CW, ...
-                for (int j = mi; j * RPP < nb; j += CW) copy_pass(e, nb, j);
+            auto copy_block = [&](int e, int nb, uint32_t half) {  // nb >= 1, warp-uniform; this warp's passes: mi, mi + CW, ...
+                for (int j = mi; j * RPP < nb; j += CW) copy_pass(e, nb, j, half);
             };
-            if (n > 0) copy_block(e0, min(n, 32));
-            if (n > 32) copy_block(e1, min(n - 32, 32));
+            if (n > 0) copy_block(e0, min(n, 32), 0u);
+            if (n > 32) copy_block(e1, min(n - 32, 32), 0u);
             for (int base = 64; base < n; base += 32)  // dense tiles and the centre offset
-                copy_block(__ldg(tl_tile + (k << 7) + base + lane), min(n - base, 32));
+                copy_block(__ldg(tl_tile + (k << 7) + base + lane), min(n - base, 32), 0u);
+            if (PAIR) {
+                if (n2 > 0) copy_block(f0, min(n2, 32), 4u);
+                if (n2 > 32) copy_block(f1, min(n2 - 32, 32), 4u);
+                for (int base = 64; base < n2; base += 32)
+                    copy_block(__ldg(tl_tile + ((k + 1) << 7) + base + lane), min(n2 - base, 32), 4u);
+            }
             // every lane: "my copies into this stage have landed" arrives asynchronously (32 CW arrivals complete it)
             cp_async_mbar_arrive_noinc_s(full0_a + 8 * st);
             TC_STAMP(warp == 0 && lane == 0 && blockIdx.x == gridDim.x / 2, 2, tstep);
@@ -520,10 +552,14 @@ __global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 
         while (st >= SA) { st -= SA; ph ^= 1; }
         while (stb >= SB) { stb -= SB; phb ^= 1; }
         while (rest) {
-            const int k = __ffs(rest) - 1;
+            const int k = PAIR ? 2 * (__ffs(rest) - 1) : __ffs(rest) - 1;
             const uint32_t m0 = __shfl_sync(0xffffffffu, mk.x, k), m1 = __shfl_sync(0xffffffffu, mk.y, k),
                            m2 = __shfl_sync(0xffffffffu, mk.z, k), m3 = __shfl_sync(0xffffffffu, mk.w, k);
             const bool any = (m0 | m1 | m2 | m3) != 0;  // warp-uniform: does THIS tile have a rule at offset k
+            // the pair's second offset (lanes >= K hold empty masks)
+            const uint32_t p0 = PAIR ? __shfl_sync(0xffffffffu, mk.x, k + 1) : 0u, p1 = PAIR ? __shfl_sync(0xffffffffu, mk.y, k + 1) : 0u,
+                           p2 = PAIR ? __shfl_sync(0xffffffffu, mk.z, k + 1) : 0u, p3 = PAIR ? __shfl_sync(0xffffffffu, mk.w, k + 1) : 0u;
+            const bool any2 = (p0 | p1 | p2 | p3) != 0;
             const int left = c_in - ch * chw;
             const int nk0 = min(kTcChunk, left) / 8;                                   // MMAs (K = 8 each) from atom 0
             const int nk1 = NA == 2 ? max(0, min(kTcChunk, left - kTcChunk)) / 8 : 0;  // ... and from atom 1
@@ -539,7 +575,12 @@ __global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 
             TC_STAMP(warp == 9 && lane == 0 && blockIdx.x == gridDim.x / 2, 3, tstep);
             const uint64_t a_desc = desc_hi | (uint64_t)((smem_u32(sA + (size_t)st * a_stage) & 0x3FFFFu) >> 4);
             if (elect_one()) {
-                if (any) {
+                if (PAIR) {  // channels [0, 16) of the rows = offset k under its mask, [16, 32) = offset k + 1 under its own
+                    if (any)
+                        for (int j = 0; j < 2; ++j) umma_tf32_masked(d, a_desc + 2 * j, b_desc + 2 * j, idesc, ~m0, ~m1, ~m2, ~m3);
+                    if (any2)
+                        for (int j = 2; j < 4; ++j) umma_tf32_masked(d, a_desc + 2 * j, b_desc + 2 * j, idesc, ~p0, ~p1, ~p2, ~p3);
+                } else if (any) {
                     for (int j = 0; j < nk0; ++j)  // + 32 bytes of K per MMA = + 2 in the address field
                         umma_tf32_masked(d, a_desc + 2 * j, b_desc + 2 * j, idesc, ~m0, ~m1, ~m2, ~m3);
                     for (int j = 0; j < nk1; ++j)  // second atom: 16 KB further in A, NT x 128 bytes further in B
