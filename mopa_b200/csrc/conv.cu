@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(256) k_dw_generic(Gather gt, const float *__re
 // the only long dimension: dW[k][ci][co] = sum_o x[in(k, o)][ci] dy[o][co] = (Xg^T dY)[k][co] with Xg[o][k] = x[in(k, o)][ci],
 // a (32 x rows) x (rows x n_out) product. mma.sync m16n8k8 takes 8 rows per step: a lane gathers its eight A values
 // (offset m = g, g + 8, g + 16, g + 24; rows t, t + 4) scalar by scalar straight into the fragment layout, dy is read once
-// per row instead of once per offset and row (k_dw_generic: 27 passes over dy, 83 us at 231k rows; this kernel: ~10 us).
+// per row instead of once per offset and row (k_dw_generic: 27 passes over dy, 83 us at 231k rows; this kernel: ~20 us).
 // grid (blocks, 1, n_in); every warp strides over 8-row chunks; warps, then blocks, are summed in index order.
 template <int NT8>
 __global__ void __launch_bounds__(256) k_dw_rows_mma(Gather gt, const float *__restrict__ in, int64_t ld_in,
@@ -570,19 +570,37 @@ __global__ void __launch_bounds__(256) k_dw_rows_mma(Gather gt, const float *__r
 #pragma unroll 2
     for (int64_t c = (int64_t)blockIdx.x * 8 + warp; c < n_chunks; c += stride) {
         const int64_t o0 = (c << 3) + t, o1 = o0 + 4;
-        uint32_t a[2][4];
+        // Branch-free: all eight rule lookups first, then all eight gathers (clamped addresses, results selected afterwards).
+        // With `if (valid) { i = lookup; if (i >= 0) x = load; }` per element the compiler emitted eight reconvergence
+        // regions, i.e. eight index -> value round trips one after the other per chunk (55 us instead of ~15).
+        int src[2][4];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int m = 16 * mt + g + 8 * (e & 1);
                 const int64_t o = (e & 2) ? o1 : o0;
-                float x = 0.f;
-                if (m < K && o < gt.n_out) {
-                    const int i = gather_lookup(gt, m, o);
-                    if (i >= 0) x = __ldg(in + (int64_t)i * ld_in + ci);
+                const bool ok = m < K && o < gt.n_out;
+                const int mc = m < K ? m : K - 1;
+                const int64_t oc = o < gt.n_out ? o : gt.n_out - 1;
+                int i;
+                if (gt.table) {  // (uniform)
+                    i = __ldg(gt.table + (int64_t)mc * gt.ld + oc);
+                } else {
+                    const int kx = __ldg(gt.kidx + oc), pr = __ldg(gt.parent + oc);
+                    i = kx == m ? pr : -1;
                 }
-                a[mt][e] = to_tf32(x);
+                src[mt][e] = ok ? i : -1;
+            }
+        }
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = src[mt][e];
+                const float x = __ldg(in + (int64_t)(i < 0 ? 0 : i) * ld_in + ci);
+                a[mt][e] = to_tf32(i < 0 ? 0.f : x);
             }
         }
 #pragma unroll
