@@ -282,6 +282,8 @@ __global__ void __launch_bounds__(256) k_conv_smallcin(Gather gt, const float *_
         for (int u = 0; u < 9; ++u) idx[u] = k0 + u < gt.volume ? gather_lookup(gt, k0 + u, o) : -1;
         for (int ci = 0; ci < c_in; ++ci) {
             float x[9];
+            // (guarded loads: absent neighbours -- ~85 % of them -- are not fetched; a branch-free variant with clamped rows
+            // was measured slower, 49 vs 43 us)
 #pragma unroll
             for (int u = 0; u < 9; ++u) x[u] = idx[u] >= 0 ? __ldg(in + (int64_t)idx[u] * ld_in + ci) : 0.f;
 #pragma unroll

@@ -193,21 +193,6 @@ __global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 
         mk0 = __ldg(gt.tm + tile0 * K + lane);
         if (n_mt == 2) mk1 = __ldg(gt.tm + (tile0 + 1) * K + lane);
     }
-    uint32_t liveset = __ballot_sync(0xffffffffu, (mk0.x | mk0.y | mk0.z | mk0.w | mk1.x | mk1.y | mk1.z | mk1.w) != 0u);
-    if (PAIR) {  // from here on a bit of the live set is a UNIT of the pipeline: the pair of offsets (2u, 2u + 1)
-        const uint32_t t = (liveset | (liveset >> 1)) & 0x15555555u;
-        uint32_t units = 0;
-#pragma unroll
-        for (int u = 0; u < 14; ++u) units |= ((t >> (2 * u)) & 1u) << u;
-        liveset = units;
-    }
-    if (S > 1) {  // this CTA's share: live offsets number blockIdx.y, blockIdx.y + S, ...
-        uint32_t mine = 0;
-        int r = 0;
-        for (uint32_t rest = liveset; rest; rest &= rest - 1, ++r)
-            if (r % S == (int)blockIdx.y) mine |= rest & (0u - rest);
-        liveset = mine;
-    }
     if (BN && tid < NT) {
         const float mu = X.bn_mean[tid], sc = X.bn_invstd[tid] * X.bn_weight[tid];
         cst[tid] = sc;
@@ -225,6 +210,22 @@ __global__ void __launch_bounds__(WIDE == 1 ? kTcMaxThreads : (WIDE == 2 ? 11 * 
             for (int q = 0; q < NT / 16; ++q) tmem_st16_zero(taddr + 16 * q);
         }
         tmem_st_wait();
+    }
+    // (the masks are consumed only here: their load latency runs under the first barrier and the TMEM zeroing)
+    uint32_t liveset = __ballot_sync(0xffffffffu, (mk0.x | mk0.y | mk0.z | mk0.w | mk1.x | mk1.y | mk1.z | mk1.w) != 0u);
+    if (PAIR) {  // from here on a bit of the live set is a UNIT of the pipeline: the pair of offsets (2u, 2u + 1)
+        const uint32_t t = (liveset | (liveset >> 1)) & 0x15555555u;
+        uint32_t units = 0;
+#pragma unroll
+        for (int u = 0; u < 14; ++u) units |= ((t >> (2 * u)) & 1u) << u;
+        liveset = units;
+    }
+    if (S > 1) {  // this CTA's share: live offsets number blockIdx.y, blockIdx.y + S, ...
+        uint32_t mine = 0;
+        int r = 0;
+        for (uint32_t rest = liveset; rest; rest &= rest - 1, ++r)
+            if (r % S == (int)blockIdx.y) mine |= rest & (0u - rest);
+        liveset = mine;
     }
     tc_fence_before_sync();
     __syncthreads();
