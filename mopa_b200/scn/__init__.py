@@ -4,6 +4,15 @@ from .modules import (AddTable, BatchNormalization, BatchNormLeakyReLU, BatchNor
                       Deconvolution, Identity, InputLayer, JoinTable, NetworkInNetwork, OutputLayer, Sequential,
                       SparseConvNetTensor, SubmanifoldConvolution, UNet)
 
+
+
+def release_arenas():
+    """Drop the idle activation / gradient / scratch arenas the compiled executor keeps across steps (they survive
+    torch.cuda.empty_cache() by design: scn/compiler.py::_ArenaPool)."""
+    from .compiler import release_arenas as _release
+    _release()
+
+
 __all__ = ["AddTable", "BatchNormalization", "BatchNormLeakyReLU", "BatchNormReLU", "ConcatTable", "Convolution",
            "Deconvolution", "Identity", "InputLayer", "JoinTable", "Metadata", "NetworkInNetwork", "OutputLayer",
-           "Sequential", "SparseConvNetTensor", "SubmanifoldConvolution", "UNet", "get_precision", "set_precision"]
+           "Sequential", "SparseConvNetTensor", "SubmanifoldConvolution", "UNet", "get_precision", "release_arenas", "set_precision"]

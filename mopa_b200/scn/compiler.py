@@ -23,6 +23,70 @@ OP_SUBM, OP_CONV, OP_DECONV, OP_BN = 1, 2, 3, 4
 
 
 
+class _ArenaPool:
+    """The executor's arenas (activations, gradients, scratch: 0.1-10 GB per pass) kept across steps instead of going back
+    to torch's caching allocator. Two reasons: MoPA's loop calls torch.cuda.empty_cache() every iteration
+    (train_xmuda_mopa.py:593), which hands every cached block back to the driver and makes the next forward cudaMalloc its
+    arenas again; and the caching allocator splits a cached multi-GB block to serve a smaller request, so that the next
+    request of the original size allocates afresh (seen as 50 ms - 1 s stalls with two steps in flight). A lease is keyed
+    by (device, stream, size class): re-use on the same stream is ordered by the stream itself, exactly like the caching
+    allocator's own re-use. At most `keep` idle tensors per key and `max_idle_bytes` in all are kept; `release()` (also
+    exported as scn.release_arenas()) drops them. MOPA_SCN_ARENA_POOL=0 turns the pool off."""
+
+    def __init__(self, keep=3, max_idle_bytes=64 << 30):
+        self.idle = {}
+        self.keep, self.max_idle_bytes, self.idle_bytes = keep, max_idle_bytes, 0
+        self.enabled = os.environ.get("MOPA_SCN_ARENA_POOL", "1") != "0"
+
+    def get(self, nbytes, dev):
+        nbytes = _arena_bytes(nbytes)
+        if not self.enabled:
+            return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, nbytes)
+        lst = self.idle.get(key)
+        if lst:
+            self.idle_bytes -= nbytes
+            return lst.pop()
+        t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        t._mopa_arena_key = key
+        return t
+
+    def put(self, t):
+        key = getattr(t, "_mopa_arena_key", None)
+        if key is None or not self.enabled:
+            return
+        lst = self.idle.setdefault(key, [])
+        if len(lst) < self.keep and self.idle_bytes + key[2] <= self.max_idle_bytes:
+            lst.append(t)
+            self.idle_bytes += key[2]
+
+    def release(self):
+        self.idle.clear()
+        self.idle_bytes = 0
+
+
+_arenas = _ArenaPool()
+
+
+def release_arenas():
+    """Drop the idle arenas of the compiled executor (they survive torch.cuda.empty_cache() by design)."""
+    _arenas.release()
+
+
+class _Lease:
+    """Returns its tensors to the arena pool when the autograd context that holds it dies."""
+
+    def __init__(self, *tensors):
+        self.tensors = tensors
+
+    def __del__(self):
+        try:
+            for t in self.tensors:
+                _arenas.put(t)
+        except Exception:  # interpreter shutdown
+            pass
+
+
 def _arena_bytes(n):
     """Arena sizes rounded up to 1/16 of their power of two: consecutive batches differ by a few per cent in size, and
     torch's caching allocator only reuses a cached block for a request of (nearly) the same size; exact sizes made it
@@ -239,14 +303,16 @@ class _ProgramFunction(Function):
             _lib.check(L.mopa_scn_Program_prepare(handle, meta._h, coords.data_ptr(), n, ncols, where, prec, stream, n_active,
                                                   sizes))
             meta.n_points = n
-            act = torch.empty(_arena_bytes(sizes[0]), dtype=torch.uint8, device=dev)
-            scratch = torch.empty(_arena_bytes(sizes[2]), dtype=torch.uint8, device=dev)
+            act = _arenas.get(sizes[0], dev)
+            scratch = _arenas.get(sizes[2], dev)
             out = torch.empty(n, prog.bufs[prog.out_buf][1], dtype=torch.float32, device=dev)
             tensors = prog.tensors()
             params = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
             _lib.check(L.mopa_scn_Program_forward(handle, meta._h, feats.data_ptr(), ld, params, 1 if train else 0, prec,
                                                   act.data_ptr(), scratch.data_ptr(), out.data_ptr(), out.shape[1], stream))
+        _arenas.put(scratch)  # (packed weights + statistics blocks: only the forward kernels just queued read them)
         ctx.prog, ctx.meta, ctx.act, ctx.train, ctx.prec = prog, meta, act, train, prec
+        ctx.lease = _Lease(act)
         ctx.sizes = (int(sizes[1]), int(sizes[2]))
         ctx.n_rows = feats.shape[0]
         # The tensors the backward pass reads (conv weights for d_input, BatchNorm weight / bias) go through
@@ -291,13 +357,15 @@ class _ProgramFunction(Function):
                 grads.append(g)
             params = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() if t is not None else None for t in tensors])
             pgrads = (ctypes.c_void_p * len(tensors))(*ptrs)
-            grad_arena = torch.empty(_arena_bytes(ctx.sizes[0]), dtype=torch.uint8, device=dev)
-            scratch = torch.empty(_arena_bytes(ctx.sizes[1]), dtype=torch.uint8, device=dev)
+            grad_arena = _arenas.get(ctx.sizes[0], dev)
+            scratch = _arenas.get(ctx.sizes[1], dev)
             d_feats = torch.zeros(ctx.n_rows, prog.in_planes, dtype=torch.float32, device=dev) if need[3] else None
             _lib.check(L.mopa_scn_Program_backward(
                 prog.handle, meta._h, params, pgrads, 1 if ctx.train else 0, ctx.prec, ctx.act.data_ptr(),
                 grad_arena.data_ptr(), scratch.data_ptr(), d_out.data_ptr(), ld_dout,
                 d_feats.data_ptr() if d_feats is not None else None, prog.in_planes, F._stream(dev)))
+            _arenas.put(grad_arena)  # (the d_weight stream has been joined: everything that touches them is queued on this stream)
+            _arenas.put(scratch)
         return (None, None, None, d_feats) + tuple(grads)
 
 

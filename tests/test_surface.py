@@ -209,3 +209,31 @@ def test_map_tensors_walks_a_mopa_data_batch():
     assert set(out) == set(batch) and isinstance(out["x"], list) and isinstance(out["nested"]["t"], tuple)
     assert torch.equal(out["x"][0], batch["x"][0] + 1) and torch.equal(out["nested"]["t"][0], torch.full((2,), 2.0))
     assert out["img_indices"][0] is batch["img_indices"][0] and out["id"] == ("a", 7)
+
+
+def test_arena_pool_keeps_and_bounds_idle_tensors():
+    """compiler._ArenaPool (host logic, exercised with CPU tensors standing in for device arenas): a returned tensor is
+    handed out again for the same key, at most `keep` idle tensors per key and `max_idle_bytes` in all are kept, tensors
+    that did not come from the pool are ignored, release() drops everything."""
+    import torch
+    from mopa_b200.scn.compiler import _ArenaPool
+    pool = _ArenaPool(keep=2, max_idle_bytes=3 << 20)
+    pool.enabled = True
+
+    def lease(nbytes):
+        t = torch.empty(nbytes, dtype=torch.uint8)
+        t._mopa_arena_key = (0, 0, nbytes)
+        return t
+    a, b, c = lease(1 << 20), lease(1 << 20), lease(1 << 20)
+    for t in (a, b, c):
+        pool.put(t)
+    assert len(pool.idle[(0, 0, 1 << 20)]) == 2 and pool.idle_bytes == 2 << 20  # keep = 2
+    big = lease(2 << 20)
+    pool.put(big)  # would exceed max_idle_bytes
+    assert (0, 0, 2 << 20) not in pool.idle or not pool.idle[(0, 0, 2 << 20)]
+    pool.put(torch.empty(8, dtype=torch.uint8))  # foreign tensor: ignored
+    assert pool.idle_bytes == 2 << 20
+    got = pool.idle[(0, 0, 1 << 20)].pop()
+    assert got is b or got is a
+    pool.release()
+    assert not pool.idle and pool.idle_bytes == 0
